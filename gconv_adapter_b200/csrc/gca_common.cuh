@@ -1,0 +1,78 @@
+// Shared host/device helpers for libgca (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gca.h"
+
+// Host-side descriptor handed out by gca_graph_build.  All pointers are device pointers
+// into the caller's workspace; the struct itself lives on the host heap.
+struct gca_graph {
+    int32_t N, row_begin, row_end, normalize;
+    int64_t E;
+    int64_t capacity;
+    int32_t* rowptr;
+    int32_t* colidx;
+    int32_t* rowptr_t;
+    int32_t* colidx_t;
+    float* dis;
+    int32_t* cnt;      // [n] counters / fill cursors (forward CSR)
+    int32_t* cnt_t;    // [n] counters / fill cursors (transposed CSR)
+    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t
+};
+
+namespace gca {
+
+extern thread_local cudaError_t tl_last_cuda_error;
+void count_launch(int n = 1);
+int num_sms();
+
+inline int record(cudaError_t e) {
+    if (e != cudaSuccess) { tl_last_cuda_error = e; return GCA_ERR_CUDA; }
+    return GCA_OK;
+}
+
+#define GCA_TRY(expr)                                   \
+    do {                                                \
+        int _st = (expr);                               \
+        if (_st != GCA_OK) return _st;                  \
+    } while (0)
+
+#define GCA_CUDA(call) GCA_TRY(::gca::record((call)))
+
+// Check the launch that was just issued (asynchronous: configuration errors only).
+#define GCA_LAUNCH_OK()                                 \
+    do {                                                \
+        ::gca::count_launch();                          \
+        GCA_CUDA(cudaGetLastError());                   \
+    } while (0)
+
+constexpr int kWarp = 32;
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+// ---- device helpers -------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// Streaming (read-once) 128-bit load: bypass L1 allocation so the gather operands keep it.
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg4_stream(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_shfl_xor(float4 v, int m) {
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+    v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+    v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+    v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+    return v;
+}
+
+}  // namespace gca

@@ -1,0 +1,787 @@
+// Forward / backward kernels of the GConv-Adapter hot path (sm_100a, fp32).
+//
+//   K1 k_project      skinny projection  [n,d] x [d,R] -> [n,R]      (conv_down.lin ; gH2 = gY Wu)
+//   K2 k_hop          r-wide gather-SpMM (+bias, act, or act')        (conv_down.propagate and its transpose)
+//   K3 k_hop_expand   r-wide gather-SpMM on a 64-row tile staged in shared memory, fused with the
+//                     [64,R] x [R,d] expansion, bias, residual and scalar epilogue
+//                     (conv_up + skip + scalar ; gP -> gX)
+//   K4 k_wgrad        weight-gradient reduction  G[R,d] = H^T A  with per-CTA partials (no atomics)
+//   K6 k_finalize     deterministic second-stage reduction of all partials
+//
+// Reference semantics: /root/reference/src/finetune/gconv_adapter.py:92-106 (see include/gca.h).
+// Sparse rows are processed by lane groups (R/4 lanes x 128-bit loads per neighbour row); rows
+// longer than kLongRow are swept by the whole warp.  All reductions have a fixed order.
+#include "gca_common.cuh"
+
+namespace gca {
+namespace {
+
+constexpr int kLongRow = 96;
+constexpr int kTileRows = 64;     // rows per CTA tile in k_hop_expand
+constexpr int kMaxParts = 320;    // per-CTA weight-gradient partials (>= 2 * 148)
+constexpr int kMaxPartsBd = 1280; // per-CTA bias-gradient partials of the transpose hop
+constexpr int kMaxFin = 256;      // CTAs of the finalize kernel
+
+struct ScratchLayout {
+    size_t header, gu, col, gd, dot, bd, gsp, total;   // byte offsets
+};
+__host__ __device__ inline ScratchLayout scratch_layout(int d, int r) {
+    ScratchLayout L;
+    size_t off = 0;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    L.header = off; off += 256;
+    // blocks whose offsets depend on r only come first (gca_bwd_hop2 does not know d)
+    L.bd = off;  off += up(sizeof(float) * (size_t)kMaxPartsBd * r);
+    L.gsp = off; off += up(sizeof(float) * (size_t)kMaxFin);
+    L.dot = off; off += up(sizeof(float) * (size_t)kMaxParts);
+    L.gu = off;  off += up(sizeof(float) * (size_t)kMaxParts * r * d);
+    L.col = off; off += up(sizeof(float) * (size_t)kMaxParts * d);
+    L.gd = off;  off += up(sizeof(float) * (size_t)kMaxParts * r * d);
+    L.total = off;
+    return L;
+}
+// header ints: [0] #partials gu/col, [1] #partials gd/dot, [2] #partials bd, [3] finalize ticket
+
+// ------------------------------------------------------------------------------------------
+// sparse row gather
+// ------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ float4 gather_rows(const float* __restrict__ F, const int* __restrict__ colidx,
+                                              int beg, int end, int stride, int sub) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = beg;
+    for (; e + 3 * stride < end; e += 4 * stride) {
+        const int j0 = __ldg(colidx + e), j1 = __ldg(colidx + e + stride);
+        const int j2 = __ldg(colidx + e + 2 * stride), j3 = __ldg(colidx + e + 3 * stride);
+        const float4 v0 = ldg4(F + (size_t)j0 * R + sub * 4);
+        const float4 v1 = ldg4(F + (size_t)j1 * R + sub * 4);
+        const float4 v2 = ldg4(F + (size_t)j2 * R + sub * 4);
+        const float4 v3 = ldg4(F + (size_t)j3 * R + sub * 4);
+        acc = f4_add(acc, v0); acc = f4_add(acc, v1); acc = f4_add(acc, v2); acc = f4_add(acc, v3);
+    }
+    for (; e < end; e += stride) {
+        const int j = __ldg(colidx + e);
+        acc = f4_add(acc, ldg4(F + (size_t)j * R + sub * 4));
+    }
+    return acc;
+}
+
+// One CSR row per lane group (R/4 lanes); every lane of the warp must call this.
+template <int R>
+__device__ __forceinline__ float4 warp_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                 const float* __restrict__ F, int row, bool valid, int lane) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    const int sub = lane % LPG, grp = lane / LPG;
+    int beg = 0, end = 0;
+    if (valid) { beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
+    const bool is_long = (end - beg) > kLongRow;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!is_long) acc = gather_rows<R>(F, colidx, beg, end, 1, sub);
+    unsigned longmask = __ballot_sync(0xffffffffu, is_long);
+    while (longmask) {                                   // warp-uniform
+        const int src = __ffs(longmask) - 1;
+        const int g = src / LPG;
+        const unsigned gm = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << (g * LPG));
+        longmask &= ~gm;
+        const int b = __shfl_sync(0xffffffffu, beg, src), e = __shfl_sync(0xffffffffu, end, src);
+        float4 part = gather_rows<R>(F, colidx, b + grp, e, GPW, sub);
+#pragma unroll
+        for (int off = LPG; off < 32; off <<= 1) part = f4_add(part, f4_shfl_xor(part, off));
+        if (grp == g) acc = part;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float act_apply(float h, int act) {
+    if (act == GCA_ACT_RELU) return h < 0.f ? 0.f : h;
+    if (act == GCA_ACT_SILU) return h / (1.f + expf(-h));
+    return h;
+}
+__device__ __forceinline__ float silu_grad(float h) {
+    const float sg = 1.f / (1.f + expf(-h));
+    return sg * (1.f + h * (1.f - sg));
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: out[i, 0:R] = rowscale[i] * s * sum_k A[i,k] W[k, 0:R]
+// Thread (kq = lane & 7, rg = lane >> 3) of warp w owns RT rows and the k-quads kq, kq+8, ...:
+// a quarter warp reads 128 contiguous bytes of one row; W sits in shared memory, padded so the
+// eight k-quads of a quarter warp hit distinct banks.  Partial sums are combined over the eight
+// kq lanes with a transposing butterfly (56 shuffles for 64 values).
+// ------------------------------------------------------------------------------------------
+template <int R, bool W_IS_RD>
+__global__ void __launch_bounds__(256, 2)
+k_project(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ rowscale,
+          const float* __restrict__ scalar, float* __restrict__ out, int n, int d) {
+    constexpr int RT = 64 / R;            // rows per thread
+    constexpr int TILE = 32 * RT;         // rows per CTA tile (8 warps x 4 row groups x RT)
+    constexpr int KS = 4 * R + 4;         // padded floats per k-quad of W
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;
+    const int nk4 = d >> 2;
+    for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
+        int k, c;
+        if (W_IS_RD) { c = idx / d; k = idx - c * d; } else { k = idx / R; c = idx - k * R; }
+        Ws[(k >> 2) * KS + (k & 3) * R + c] = W[idx];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kq = lane & 7, rg = lane >> 3;
+    const float s = scalar ? __ldg(scalar) : 1.f;
+    const int ntiles = (n + TILE - 1) / TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * TILE + (warp * 4 + rg) * RT;
+        const float* arow[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) arow[t] = A + (size_t)min(row0 + t, n - 1) * lda;
+        float v[RT * R];
+#pragma unroll
+        for (int i = 0; i < RT * R; ++i) v[i] = 0.f;
+        float4 a[RT];
+        if (kq < nk4) {
+#pragma unroll
+            for (int t = 0; t < RT; ++t) a[t] = ldg4_stream(arow[t] + kq * 4);
+        }
+        for (int k4 = kq; k4 < nk4; k4 += 8) {
+            float4 an[RT];
+            const int k4n = k4 + 8;
+            if (k4n < nk4) {
+#pragma unroll
+                for (int t = 0; t < RT; ++t) an[t] = ldg4_stream(arow[t] + k4n * 4);
+            }
+            const float* w = Ws + k4 * KS;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int c4 = 0; c4 < R / 4; ++c4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(w + kk * R + c4 * 4);
+#pragma unroll
+                    for (int t = 0; t < RT; ++t) {
+                        const float av = kk == 0 ? a[t].x : kk == 1 ? a[t].y : kk == 2 ? a[t].z : a[t].w;
+                        v[t * R + c4 * 4 + 0] = fmaf(av, wv.x, v[t * R + c4 * 4 + 0]);
+                        v[t * R + c4 * 4 + 1] = fmaf(av, wv.y, v[t * R + c4 * 4 + 1]);
+                        v[t * R + c4 * 4 + 2] = fmaf(av, wv.z, v[t * R + c4 * 4 + 2]);
+                        v[t * R + c4 * 4 + 3] = fmaf(av, wv.w, v[t * R + c4 * 4 + 3]);
+                    }
+                }
+            }
+            if (k4n < nk4) {
+#pragma unroll
+                for (int t = 0; t < RT; ++t) a[t] = an[t];
+            }
+        }
+        // transposing butterfly over lane bits 2,1,0: 64 -> 32 -> 16 -> 8 values per lane
+#pragma unroll
+        for (int half = 32, bit = 4; half >= 8; half >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float send = up ? v[i] : v[i + half];
+                const float keep = up ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+        }
+        const int base = ((lane >> 2) & 1) * 32 + ((lane >> 1) & 1) * 16 + (lane & 1) * 8;
+        const int row = row0 + base / R, c0 = base % R;
+        if (row < n) {
+            const float sc = (rowscale ? __ldg(rowscale + row) : 1.f) * s;
+            float* o = out + (size_t)row * R + c0;
+            *reinterpret_cast<float4*>(o) = make_float4(v[0] * sc, v[1] * sc, v[2] * sc, v[3] * sc);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] * sc, v[5] * sc, v[6] * sc, v[7] * sc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: one r-wide hop.  FWD:  Z'[i] = dis[i] * act(dis[i] * sum_j F[j] + b)      (H1 saved for silu)
+//                      BWD:  gH1'[j] = dis[j] * act'(.) * dis[j] * sum_i F[i]   (+ per-CTA sum for gbd)
+// ------------------------------------------------------------------------------------------
+template <int R, bool BWD>
+__global__ void __launch_bounds__(256)
+k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
+      const float* __restrict__ F, const float* __restrict__ bias, int act,
+      const float* __restrict__ Zp_saved, const float* __restrict__ H1_saved,
+      float* __restrict__ out, float* __restrict__ H1_out, float* __restrict__ part_bd, int* header, int n) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPG, grp = lane / LPG;
+    const int wglobal = blockIdx.x * (blockDim.x >> 5) + warp, wtotal = gridDim.x * (blockDim.x >> 5);
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!BWD && bias) b4 = ldg4(bias + sub * 4);
+    float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rowbase = wglobal * GPW; rowbase < n; rowbase += wtotal * GPW) {
+        const int row = rowbase + grp;
+        const bool valid = row < n;
+        const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+        if (!valid) continue;
+        const float di = __ldg(dis + row);
+        const size_t o = (size_t)row * R + sub * 4;
+        if (!BWD) {
+            float4 h = make_float4(fmaf(di, acc.x, b4.x), fmaf(di, acc.y, b4.y), fmaf(di, acc.z, b4.z), fmaf(di, acc.w, b4.w));
+            if (H1_out) *reinterpret_cast<float4*>(H1_out + o) = h;
+            h = make_float4(act_apply(h.x, act), act_apply(h.y, act), act_apply(h.z, act), act_apply(h.w, act));
+            *reinterpret_cast<float4*>(out + o) = f4_scale(h, di);
+        } else {
+            float4 g = f4_scale(acc, di);
+            if (act == GCA_ACT_RELU) {
+                const float4 z = ldg4(Zp_saved + o);
+                g = make_float4(z.x > 0.f ? g.x : 0.f, z.y > 0.f ? g.y : 0.f, z.z > 0.f ? g.z : 0.f, z.w > 0.f ? g.w : 0.f);
+            } else if (act == GCA_ACT_SILU) {
+                const float4 h = ldg4(H1_saved + o);
+                g = make_float4(g.x * silu_grad(h.x), g.y * silu_grad(h.y), g.z * silu_grad(h.z), g.w * silu_grad(h.w));
+            }
+            gb = f4_add(gb, g);
+            *reinterpret_cast<float4*>(out + o) = f4_scale(g, di);
+        }
+    }
+    if (BWD) {
+        __shared__ float s_gb[8][R];
+#pragma unroll
+        for (int off = LPG; off < 32; off <<= 1) gb = f4_add(gb, f4_shfl_xor(gb, off));
+        if (grp == 0) *reinterpret_cast<float4*>(&s_gb[warp][sub * 4]) = gb;
+        __syncthreads();
+        if (threadIdx.x < R) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += s_gb[w][threadIdx.x];
+            part_bd[(size_t)blockIdx.x * R + threadIdx.x] = t;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) header[2] = gridDim.x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: tile of 64 rows: H[i] = dis[i] * sum_j F[j] staged in shared memory (and saved), then
+//     Out[i, :] = alpha * (H[i] W + bias) + beta * Resid[i, :]
+// W is kept transposed in shared memory as WT[c][k] so a warp reads 512 contiguous bytes per c.
+// Warp w owns rows 8w..8w+7 of the tile, lane l the column quads l, l+32, ...
+// ------------------------------------------------------------------------------------------
+template <int R, bool W_IS_DR>
+__global__ void __launch_bounds__(256, 2)
+k_hop_expand(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
+             const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
+             const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
+             int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
+             int n, int d) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    extern __shared__ __align__(16) float smem[];
+    float* WT = smem;                 // [R][d]
+    float* Hs = smem + (size_t)R * d; // [kTileRows][R]
+    if (Out) {
+        for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
+            if (W_IS_DR) { const int k = idx / R, c = idx - k * R; WT[c * d + k] = W[idx]; }
+            else WT[idx] = W[idx];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPG, grp = lane / LPG;
+    const float s = scalar ? __ldg(scalar) : 1.f;
+    const float alpha = alpha_is_scalar ? s : 1.f;
+    const float beta = use_resid ? s : 0.f;
+    const int nq = d >> 2;
+    const int ntiles = (n + kTileRows - 1) / kTileRows;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int trow = tile * kTileRows;
+        __syncthreads();              // WT ready / previous tile's readers of Hs are done
+        for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
+            const int row = trow + rr + grp;
+            const bool valid = row < n;
+            const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                h = f4_scale(acc, __ldg(dis + row));
+                *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
+            }
+            *reinterpret_cast<float4*>(Hs + (rr + grp) * R + sub * 4) = h;
+        }
+        __syncthreads();
+        if (!Out) continue;
+        const int r0 = trow + warp * 8;
+        const float* hs = Hs + warp * 8 * R;
+        for (int q = lane; q < nq; q += 32) {
+            float4 xr[8];
+            if (use_resid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    xr[i] = (r0 + i < n) ? ldg4_stream(resid + (size_t)(r0 + i) * ldr + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c4 = 0; c4 < R / 4; ++c4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(WT + (c4 * 4 + 0) * d + q * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(WT + (c4 * 4 + 1) * d + q * 4);
+                const float4 w2 = *reinterpret_cast<const float4*>(WT + (c4 * 4 + 2) * d + q * 4);
+                const float4 w3 = *reinterpret_cast<const float4*>(WT + (c4 * 4 + 3) * d + q * 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 h = *reinterpret_cast<const float4*>(hs + i * R + c4 * 4);
+                    acc[i].x = fmaf(h.x, w0.x, acc[i].x); acc[i].y = fmaf(h.x, w0.y, acc[i].y);
+                    acc[i].z = fmaf(h.x, w0.z, acc[i].z); acc[i].w = fmaf(h.x, w0.w, acc[i].w);
+                    acc[i].x = fmaf(h.y, w1.x, acc[i].x); acc[i].y = fmaf(h.y, w1.y, acc[i].y);
+                    acc[i].z = fmaf(h.y, w1.z, acc[i].z); acc[i].w = fmaf(h.y, w1.w, acc[i].w);
+                    acc[i].x = fmaf(h.z, w2.x, acc[i].x); acc[i].y = fmaf(h.z, w2.y, acc[i].y);
+                    acc[i].z = fmaf(h.z, w2.z, acc[i].z); acc[i].w = fmaf(h.z, w2.w, acc[i].w);
+                    acc[i].x = fmaf(h.w, w3.x, acc[i].x); acc[i].y = fmaf(h.w, w3.y, acc[i].y);
+                    acc[i].z = fmaf(h.w, w3.z, acc[i].z); acc[i].w = fmaf(h.w, w3.w, acc[i].w);
+                }
+            }
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) b4 = ldg4(bias + q * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (r0 + i >= n) continue;
+                float4 y = make_float4(alpha * (acc[i].x + b4.x), alpha * (acc[i].y + b4.y),
+                                       alpha * (acc[i].z + b4.z), alpha * (acc[i].w + b4.w));
+                if (use_resid) {
+                    y.x = fmaf(beta, xr[i].x, y.x); y.y = fmaf(beta, xr[i].y, y.y);
+                    y.z = fmaf(beta, xr[i].z, y.z); y.w = fmaf(beta, xr[i].w, y.w);
+                }
+                stg4_stream(Out + (size_t)(r0 + i) * ldo + q * 4, y);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: G[c, col0 + k] = sum_i H[i, c] A[i, col0 + k]   (+ colsum[k] = sum_i A[i,k], dot = sum A.B)
+// for the dsub columns starting at col0.  Warp = (column chunk of 128, block of CW <= 16 c's, row
+// subset); lane = one column quad.  Each CTA keeps its accumulators in registers across all its
+// row blocks and emits ONE partial per launch (no atomics, fixed order).
+// ------------------------------------------------------------------------------------------
+constexpr int kWgRows = 128;   // rows of H staged per block
+
+template <int R>
+__global__ void __launch_bounds__(384)
+k_wgrad(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, const float* __restrict__ B, int64_t ldb,
+        float* __restrict__ partG, float* __restrict__ partCol, float* __restrict__ partDot, int* header, int header_slot,
+        int n, int d, int col0, int dsub, int nchunks, int RS) {
+    constexpr int CW = R < 16 ? R : 16;   // c's per warp
+    constexpr int CB = R / CW;            // c blocks
+    extern __shared__ __align__(16) float smem[];
+    float* Hs = smem;                     // [kWgRows][R], later reused as G[R][dsub] + colsum[dsub]
+    __shared__ float s_dot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = warp % nchunks;
+    const int cb = (warp / nchunks) % CB;
+    const int rs = warp / (nchunks * CB);
+    const int q = chunk * 32 + lane;      // column quad inside [col0, col0 + dsub)
+    const bool active = q < (dsub >> 2);
+    const bool lead = cb == 0;            // this warp also owns colsum / dot for its columns
+    const float* Ac = A + col0 + q * 4;
+    const float* Bc = B ? B + col0 + q * 4 : nullptr;
+    float4 acc[CW];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dot = 0.f;
+    const int nblocks = (n + kWgRows - 1) / kWgRows;
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int row0 = blk * kWgRows;
+        const int rows = min(kWgRows, n - row0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < rows * (R / 4); idx += blockDim.x)
+            reinterpret_cast<float4*>(Hs)[idx] = ldg4(H + (size_t)row0 * R + idx * 4);
+        __syncthreads();
+        if (!active) continue;
+        for (int i0 = rs; i0 < rows; i0 += 4 * RS) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * RS;
+                if (i < rows) {
+                    a[u] = ldg4_stream(Ac + (size_t)(row0 + i) * lda);
+                    if (Bc && lead) b[u] = ldg4_stream(Bc + (size_t)(row0 + i) * ldb);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * RS;
+                if (i >= rows) break;       // warp-uniform
+                const float* hrow = Hs + i * R + cb * CW;
+#pragma unroll
+                for (int c4 = 0; c4 < CW / 4; ++c4) {
+                    const float4 h = *reinterpret_cast<const float4*>(hrow + c4 * 4);
+                    const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4& g = acc[c4 * 4 + j];
+                        g.x = fmaf(hv[j], a[u].x, g.x); g.y = fmaf(hv[j], a[u].y, g.y);
+                        g.z = fmaf(hv[j], a[u].z, g.z); g.w = fmaf(hv[j], a[u].w, g.w);
+                    }
+                }
+                if (lead) {
+                    csum = f4_add(csum, a[u]);
+                    if (Bc) dot = fmaf(a[u].x, b[u].x, fmaf(a[u].y, b[u].y, fmaf(a[u].z, b[u].z, fmaf(a[u].w, b[u].w, dot))));
+                }
+            }
+        }
+    }
+    // combine the RS row subsets in a fixed order through shared memory
+    float* G = smem;                         // [R][dsub]
+    float* Cs = smem + (size_t)R * dsub;     // [dsub]
+    for (int turn = 0; turn < RS; ++turn) {
+        __syncthreads();
+        if (rs == turn && active) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+                float4* g = reinterpret_cast<float4*>(G + (size_t)(cb * CW + c) * dsub + q * 4);
+                *g = turn == 0 ? acc[c] : f4_add(*g, acc[c]);
+            }
+            if (lead) {
+                float4* cs = reinterpret_cast<float4*>(Cs + q * 4);
+                *cs = turn == 0 ? csum : f4_add(*cs, csum);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (lane == 0) s_dot[warp] = dot;
+    __syncthreads();
+    const int nq = dsub >> 2;
+    float* pg = partG + (size_t)blockIdx.x * R * d + col0;
+    for (int idx = threadIdx.x; idx < R * nq; idx += blockDim.x) {
+        const int c = idx / nq, qq = idx - c * nq;
+        *reinterpret_cast<float4*>(pg + (size_t)c * d + qq * 4) = *reinterpret_cast<const float4*>(G + (size_t)c * dsub + qq * 4);
+    }
+    if (partCol)
+        for (int idx = threadIdx.x; idx < nq; idx += blockDim.x)
+            *reinterpret_cast<float4*>(partCol + (size_t)blockIdx.x * d + col0 + idx * 4) = *reinterpret_cast<const float4*>(Cs + idx * 4);
+    if (threadIdx.x == 0) {
+        if (partDot) {
+            float t = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_dot[w];
+            if (col0 == 0) partDot[blockIdx.x] = t; else partDot[blockIdx.x] += t;   // launches are stream-ordered
+        }
+        if (blockIdx.x == 0) header[header_slot] = gridDim.x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: sum the partials in index order; the last CTA to finish adds up the gscalar pieces.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, const float* __restrict__ partGd,
+           const float* __restrict__ partDot, const float* __restrict__ partBd, float* gsp, int* header,
+           const float* __restrict__ Wu, const float* __restrict__ bu, const float* __restrict__ scalar, int skip,
+           float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar, int d, int r) {
+    const int pu = header[0], pd = header[1], pb = header[2];
+    const float s = scalar ? __ldg(scalar) : 1.f;
+    const int rd = r * d;
+    float gs = 0.f;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rd; idx += gridDim.x * blockDim.x) {
+        const int c = idx / d, k = idx - c * d;
+        float gu = 0.f;
+        for (int p = 0; p < pu; ++p) gu += partGu[(size_t)p * rd + idx];
+        if (gWu) gWu[(size_t)k * r + c] = s * gu;
+        gs = fmaf(gu, __ldg(Wu + (size_t)k * r + c), gs);
+        if (gWd) {
+            float gd = 0.f;
+            for (int p = 0; p < pd; ++p) gd += partGd[(size_t)p * rd + idx];
+            gWd[idx] = gd;
+        }
+        if (idx < d) {
+            float cs = 0.f;
+            for (int p = 0; p < pu; ++p) cs += partCol[(size_t)p * d + idx];
+            if (gbu) gbu[idx] = s * cs;
+            gs = fmaf(cs, __ldg(bu + idx), gs);
+        }
+        if (idx < r && gbd) {
+            float t = 0.f;
+            for (int p = 0; p < pb; ++p) t += partBd[(size_t)p * r + idx];
+            gbd[idx] = t;
+        }
+    }
+    if (!gscalar) return;
+    if (skip && blockIdx.x == 0)
+        for (int p = threadIdx.x; p < pd; p += blockDim.x) gs += partDot[p];
+    __shared__ float s_red[256];
+    __shared__ int s_last;
+    s_red[threadIdx.x] = gs;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        gsp[blockIdx.x] = s_red[0];
+        __threadfence();
+        s_last = (atomicAdd(&header[3], 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        float t = 0.f;
+        for (int b = 0; b < (int)gridDim.x; ++b) t += reinterpret_cast<volatile float*>(gsp)[b];
+        *gscalar = t;
+        header[3] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) GCA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return GCA_OK;
+}
+
+inline bool shape_ok(int d, int r) { return d > 0 && (d % 4) == 0 && (r == 8 || r == 16 || r == 32 || r == 64); }
+
+template <int R, bool W_IS_RD>
+int launch_project(const float* A, int64_t lda, const float* W, const float* rowscale, const float* scalar,
+                   float* out, int n, int d, cudaStream_t st) {
+    if (n == 0) return GCA_OK;
+    constexpr int TILE = 32 * (64 / R);
+    const size_t smem = sizeof(float) * (size_t)(d / 4) * (4 * R + 4);
+    if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
+    GCA_TRY(set_smem(k_project<R, W_IS_RD>, smem));
+    const int ntiles = (n + TILE - 1) / TILE;
+    const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
+    k_project<R, W_IS_RD><<<grid, 256, smem, st>>>(A, lda, W, rowscale, scalar, out, n, d);
+    GCA_LAUNCH_OK();
+    return GCA_OK;
+}
+
+template <int R, bool BWD>
+int launch_hop(const int* rowptr, const int* colidx, const float* dis, const float* F, const float* bias, int act,
+               const float* Zp, const float* H1s, float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st) {
+    constexpr int GPW = 32 / (R / 4);
+    int grid = (n + 8 * GPW - 1) / (8 * GPW);
+    const int cap = BWD ? (kMaxPartsBd < 8 * num_sms() ? kMaxPartsBd : 8 * num_sms()) : 8 * num_sms();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k_hop<R, BWD><<<grid, 256, 0, st>>>(rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n);
+    GCA_LAUNCH_OK();
+    return GCA_OK;
+}
+
+template <int R, bool W_IS_DR>
+int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, const float* F, const float* W,
+                      const float* bias, const float* resid, int64_t ldr, const float* scalar, int alpha_is_scalar,
+                      int use_resid, float* Hout, float* Out, int64_t ldo, int n, int d, cudaStream_t st) {
+    if (n == 0) return GCA_OK;
+    const size_t smem = sizeof(float) * ((size_t)R * d + (size_t)kTileRows * R);
+    if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
+    GCA_TRY(set_smem(k_hop_expand<R, W_IS_DR>, smem));
+    const int ntiles = (n + kTileRows - 1) / kTileRows;
+    const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
+    k_hop_expand<R, W_IS_DR><<<grid, 256, smem, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
+                                                       alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+    GCA_LAUNCH_OK();
+    return GCA_OK;
+}
+
+template <int R>
+int launch_wgrad(const float* A, int64_t lda, const float* H, const float* B, int64_t ldb, float* partG, float* partCol,
+                 float* partDot, int* header, int slot, int n, int d, cudaStream_t st) {
+    constexpr int CW = R < 16 ? R : 16, CB = R / CW;
+    constexpr int kMaxWarps = 12;
+    const int max_chunks = kMaxWarps / CB;                 // column chunks (128 wide) per launch
+    const int nblocks = (n + kWgRows - 1) / kWgRows;
+    int grid = nblocks < 1 ? 1 : nblocks;
+    const int cap = kMaxParts < 2 * num_sms() ? kMaxParts : 2 * num_sms();
+    if (grid > cap) grid = cap;
+    for (int col0 = 0; col0 < d; col0 += max_chunks * 128) {
+        const int dsub = (d - col0) < max_chunks * 128 ? (d - col0) : max_chunks * 128;
+        const int nchunks = (dsub / 4 + 31) / 32;
+        int RS = kMaxWarps / (nchunks * CB);
+        if (RS < 1) RS = 1;
+        const int warps = nchunks * CB * RS;
+        const size_t smem_h = sizeof(float) * (size_t)kWgRows * R;
+        const size_t smem_g = sizeof(float) * ((size_t)R * dsub + dsub);
+        const size_t smem = smem_h > smem_g ? smem_h : smem_g;
+        if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
+        GCA_TRY(set_smem(k_wgrad<R>, smem));
+        k_wgrad<R><<<grid, warps * 32, smem, st>>>(A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d,
+                                                    col0, dsub, nchunks, RS);
+        GCA_LAUNCH_OK();
+    }
+    return GCA_OK;
+}
+
+#define GCA_DISPATCH_R(r, CALL)                         \
+    switch (r) {                                        \
+        case 8:  { constexpr int R_ = 8;  return CALL; }  \
+        case 16: { constexpr int R_ = 16; return CALL; }  \
+        case 32: { constexpr int R_ = 32; return CALL; }  \
+        case 64: { constexpr int R_ = 64; return CALL; }  \
+        default: return GCA_ERR_UNSUPPORTED;            \
+    }
+
+}  // namespace
+}  // namespace gca
+
+using namespace gca;
+
+extern "C" int gca_shape_is_fast(int32_t d, int32_t r) { return shape_ok(d, r) ? 1 : 0; }
+
+extern "C" int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, const float* Wd, float* Pp_local,
+                               int32_t d, int32_t r, gca_stream_t stream) {
+    if (!g || !X || !Wd || !Pp_local || ldx < d) return GCA_ERR_INVALID_ARG;
+    if (!shape_ok(d, r) || (ldx % 4) != 0) return GCA_ERR_UNSUPPORTED;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GCA_DISPATCH_R(r, (launch_project<R_, true>(X, ldx, Wd, g->dis, nullptr, Pp_local, n, d, st)));
+}
+
+extern "C" int gca_fwd_hop1(const gca_graph* g, const float* Pp_full, const float* bd, int act, float* Zp_local,
+                            float* H1_local, int32_t r, gca_stream_t stream) {
+    if (!g || !Pp_full || !bd || !Zp_local) return GCA_ERR_INVALID_ARG;
+    if (act < GCA_ACT_NONE || act > GCA_ACT_SILU) return GCA_ERR_INVALID_ARG;
+    if (act == GCA_ACT_SILU && !H1_local) return GCA_ERR_INVALID_ARG;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GCA_DISPATCH_R(r, (launch_hop<R_, false>(g->rowptr, g->colidx, g->dis, Pp_full, bd, act, nullptr, nullptr,
+                                             Zp_local, H1_local, nullptr, nullptr, n, st)));
+}
+
+extern "C" int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full, const float* X, int64_t ldx, const float* Wu,
+                               const float* bu, const float* scalar, int skip, float* H2_local, float* Y, int64_t ldy,
+                               int32_t d, int32_t r, gca_stream_t stream) {
+    if (!g || !Zp_full || !Wu || !bu || !H2_local || !Y || ldy < d) return GCA_ERR_INVALID_ARG;
+    if (skip && (!X || ldx < d)) return GCA_ERR_INVALID_ARG;
+    if (!shape_ok(d, r) || (ldy % 4) != 0 || (skip && (ldx % 4) != 0)) return GCA_ERR_UNSUPPORTED;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GCA_DISPATCH_R(r, (launch_hop_expand<R_, true>(g->rowptr, g->colidx, g->dis, Zp_full, Wu, bu, X, ldx, scalar, 1,
+                                                   skip ? 1 : 0, H2_local, Y, ldy, n, d, st)));
+}
+
+
+extern "C" size_t gca_bwd_scratch_bytes(int32_t d, int32_t r) {
+    if (d <= 0 || r <= 0) return 0;
+    return scratch_layout(d, r).total;
+}
+
+namespace {
+struct Scratch {
+    int* header;
+    float *gu, *col, *gd, *dot, *bd, *gsp;
+};
+Scratch scratch_ptrs(void* scratch, int d, int r) {
+    const ScratchLayout L = scratch_layout(d, r);
+    char* b = static_cast<char*>(scratch);
+    return Scratch{reinterpret_cast<int*>(b + L.header), reinterpret_cast<float*>(b + L.gu),
+                   reinterpret_cast<float*>(b + L.col), reinterpret_cast<float*>(b + L.gd),
+                   reinterpret_cast<float*>(b + L.dot), reinterpret_cast<float*>(b + L.bd),
+                   reinterpret_cast<float*>(b + L.gsp)};
+}
+
+template <int R>
+int bwd_up_impl(const gca_graph* g, const float* gY, int64_t ldg, const float* H2, const float* Wu, const float* scalar,
+                float* gH2p, const Scratch& S, int n, int d, cudaStream_t st) {
+    GCA_TRY((launch_project<R, false>(gY, ldg, Wu, g->dis, scalar, gH2p, n, d, st)));
+    return launch_wgrad<R>(gY, ldg, H2, nullptr, 0, S.gu, S.col, nullptr, S.header, 0, n, d, st);
+}
+
+template <int R>
+int bwd_hop1_down_impl(const gca_graph* g, const float* gH1p_full, const float* X, int64_t ldx, const float* gY,
+                       int64_t ldg, const float* Wd, const float* scalar, int skip, float* gP, float* gX, int64_t ldgx,
+                       const Scratch& S, int n, int d, cudaStream_t st) {
+    GCA_TRY((launch_hop_expand<R, false>(g->rowptr_t, g->colidx_t, g->dis, gH1p_full, Wd, nullptr, gY, ldg, scalar, 0,
+                                         skip ? 1 : 0, gP, gX, ldgx, n, d, st)));
+    const bool want_dot = skip && scalar;
+    return launch_wgrad<R>(X, ldx, gP, want_dot ? gY : nullptr, ldg, S.gd, nullptr, want_dot ? S.dot : nullptr,
+                           S.header, 1, n, d, st);
+}
+}  // namespace
+
+extern "C" int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, const float* Wu,
+                          const float* scalar, float* gH2p_local, void* scratch, int32_t d, int32_t r,
+                          gca_stream_t stream) {
+    if (!g || !gY || !H2_local || !Wu || !gH2p_local || !scratch || ldg < d) return GCA_ERR_INVALID_ARG;
+    if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Scratch S = scratch_ptrs(scratch, d, r);
+    GCA_CUDA(cudaMemsetAsync(S.header, 0, 256, st));
+    GCA_DISPATCH_R(r, (bwd_up_impl<R_>(g, gY, ldg, H2_local, Wu, scalar, gH2p_local, S, n, d, st)));
+}
+
+extern "C" int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full, const float* Zp_local, const float* H1_local,
+                            int act, float* gH1p_local, void* scratch, int32_t r, gca_stream_t stream) {
+    if (!g || !gH2p_full || !gH1p_local || !scratch) return GCA_ERR_INVALID_ARG;
+    if (act < GCA_ACT_NONE || act > GCA_ACT_SILU) return GCA_ERR_INVALID_ARG;
+    if ((act == GCA_ACT_RELU && !Zp_local) || (act == GCA_ACT_SILU && !H1_local)) return GCA_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Scratch S = scratch_ptrs(scratch, 4, r);      // header / bd offsets do not depend on d
+    GCA_DISPATCH_R(r, (launch_hop<R_, true>(g->rowptr_t, g->colidx_t, g->dis, gH2p_full, nullptr, act, Zp_local,
+                                            H1_local, gH1p_local, nullptr, S.bd, S.header, n, st)));
+}
+
+extern "C" int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full, const float* X, int64_t ldx,
+                                 const float* gY, int64_t ldg, const float* Wd, const float* scalar, int skip,
+                                 float* gP_local, float* gX, int64_t ldgx, void* scratch, int32_t d, int32_t r,
+                                 gca_stream_t stream) {
+    if (!g || !gH1p_full || !X || !Wd || !gP_local || !scratch || ldx < d) return GCA_ERR_INVALID_ARG;
+    if (skip && (!gY || ldg < d)) return GCA_ERR_INVALID_ARG;
+    if (gX && ldgx < d) return GCA_ERR_INVALID_ARG;
+    if (!shape_ok(d, r) || (ldx % 4) != 0 || (skip && (ldg % 4) != 0) || (gX && (ldgx % 4) != 0)) return GCA_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Scratch S = scratch_ptrs(scratch, d, r);
+    GCA_DISPATCH_R(r, (bwd_hop1_down_impl<R_>(g, gH1p_full, X, ldx, gY, ldg, Wd, scalar, skip, gP_local, gX, ldgx, S, n, d, st)));
+}
+
+extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const float* bu, const float* scalar, int skip,
+                                float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar, int32_t d, int32_t r,
+                                gca_stream_t stream) {
+    if (!scratch || !Wu || !bu || d <= 0 || r <= 0) return GCA_ERR_INVALID_ARG;
+    const Scratch S = scratch_ptrs(const_cast<void*>(scratch), d, r);
+    int grid = (r * d + 255) / 256;
+    if (grid > kMaxFin) grid = kMaxFin;
+    k_finalize<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S.gu, S.col, S.gd, S.dot, S.bd, S.gsp, S.header, Wu, bu,
+                                                                     scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r);
+    GCA_LAUNCH_OK();
+    return GCA_OK;
+}
+
+// ---------------- single-GPU conveniences ----------------
+extern "C" size_t gca_forward_workspace_bytes(int32_t n, int32_t d, int32_t r) {
+    (void)d;
+    return align_up(sizeof(float) * (size_t)(n > 0 ? n : 1) * r);
+}
+
+extern "C" int gca_forward(const gca_graph* g, const float* X, int64_t ldx, const float* Wd, const float* bd,
+                           const float* Wu, const float* bu, const float* scalar, int act, int skip, void* workspace,
+                           float* Zp_save, float* H1_save, float* H2_save, float* Y, int64_t ldy, int32_t d, int32_t r,
+                           gca_stream_t stream) {
+    if (!g || !workspace) return GCA_ERR_INVALID_ARG;
+    if (g->row_begin != 0 || g->row_end != g->N) return GCA_ERR_INVALID_ARG;   // partitioned graphs use the phases
+    float* Pp = static_cast<float*>(workspace);
+    GCA_TRY(gca_fwd_project(g, X, ldx, Wd, Pp, d, r, stream));
+    GCA_TRY(gca_fwd_hop1(g, Pp, bd, act, Zp_save, H1_save, r, stream));
+    return gca_fwd_hop2_up(g, Zp_save, X, ldx, Wu, bu, scalar, skip, H2_save, Y, ldy, d, r, stream);
+}
+
+extern "C" size_t gca_backward_workspace_bytes(int32_t n, int32_t d, int32_t r) {
+    const size_t rw = align_up(sizeof(float) * (size_t)(n > 0 ? n : 1) * r);
+    return 3 * rw + gca_bwd_scratch_bytes(d, r);
+}
+
+extern "C" int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, const float* X, int64_t ldx,
+                            const float* Zp_save, const float* H1_save, const float* H2_save, const float* Wd,
+                            const float* Wu, const float* bu, const float* scalar, int act, int skip, void* workspace,
+                            float* gX, int64_t ldgx, float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar,
+                            int32_t d, int32_t r, gca_stream_t stream) {
+    if (!g || !workspace) return GCA_ERR_INVALID_ARG;
+    if (g->row_begin != 0 || g->row_end != g->N) return GCA_ERR_INVALID_ARG;
+    const int n = g->N;
+    const size_t rw = align_up(sizeof(float) * (size_t)(n > 0 ? n : 1) * r);
+    char* b = static_cast<char*>(workspace);
+    float* gH2p = reinterpret_cast<float*>(b);
+    float* gH1p = reinterpret_cast<float*>(b + rw);
+    float* gP = reinterpret_cast<float*>(b + 2 * rw);
+    void* scratch = b + 3 * rw;
+    GCA_TRY(gca_bwd_up(g, gY, ldg, H2_save, Wu, scalar, gH2p, scratch, d, r, stream));
+    GCA_TRY(gca_bwd_hop2(g, gH2p, Zp_save, H1_save, act, gH1p, scratch, r, stream));
+    GCA_TRY(gca_bwd_hop1_down(g, gH1p, X, ldx, gY, ldg, Wd, scalar, skip, gP, gX, ldgx, scratch, d, r, stream));
+    return gca_bwd_finalize(scratch, Wu, bu, scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r, stream);
+}

@@ -1,0 +1,271 @@
+"""Drop-in ``GConvAdapter`` backed by the sm_100a kernels of libgca.
+
+Mirrors /root/reference/src/finetune/gconv_adapter.py:5-108: same constructor arguments and
+defaults (:23-26), same ``ValueError`` messages (:37,51,61), same parameter names and
+``state_dict`` keys (``scalar``, ``conv_down.bias``, ``conv_down.lin.weight``,
+``conv_up.bias``, ``conv_up.lin.weight`` [, ``normalization.*``]), same near-identity init
+(:73-78, drawing from the torch RNG in the order PyG's constructors + the reference do), same
+call signature ``forward(x, edge_index, edge_attr=None)`` (:80) with ``edge_attr`` ignored, x of
+shape ``[N, d]`` or ``[1, N, d]``, and the same op order skip -> normalization -> scalar
+(:94-106).  The arithmetic runs as hand-written CUDA (include/gca.h); there is NO CPU path:
+a CPU tensor, or a missing libgca.so, raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _cabi
+from ..graphs.csr import GLOBAL_GRAPH_CACHE, GraphCache, GraphStructure
+
+_FAST_RANKS = (8, 16, 32, 64)
+
+# Test hook: when True the autograd function keeps references to the tensors it saved for the
+# backward (scaled activations Z' and H2) in ``LAST_SAVED`` so parity tests can read the ReLU mask.
+DEBUG_KEEP_SAVED = False
+LAST_SAVED: dict = {}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _GConvAdapterFunction(torch.autograd.Function):
+    """Y = s * (Ahat act(Ahat X Wd^T + bd) Wu^T + bu [+ X]) and its gradients, one graph handle."""
+
+    @staticmethod
+    def forward(ctx, x, w_down, b_down, w_up, b_up, scalar, graph: GraphStructure, act: int, skip: bool):
+        lib = _cabi.load()
+        n, d = x.shape
+        r = w_down.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            w_down, b_down, w_up, b_up = (t.contiguous() for t in (w_down, b_down, w_up, b_up))
+            y = torch.empty((n, d), dtype=torch.float32, device=dev)
+            zp = torch.empty((n, r), dtype=torch.float32, device=dev)
+            h2 = torch.empty((n, r), dtype=torch.float32, device=dev)
+            h1 = torch.empty((n, r), dtype=torch.float32, device=dev) if act == _cabi.ACT["silu"] else None
+            ws = torch.empty(lib.gca_forward_workspace_bytes(n, d, r), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.gca_forward(graph.handle, x.data_ptr(), x.stride(0), w_down.data_ptr(), b_down.data_ptr(),
+                                        w_up.data_ptr(), b_up.data_ptr(), _ptr(scalar), act, int(skip), ws.data_ptr(),
+                                        zp.data_ptr(), _ptr(h1), h2.data_ptr(), y.data_ptr(), y.stride(0), d, r,
+                                        stream), "gca_forward")
+        ctx.graph, ctx.act, ctx.skip = graph, act, skip
+        ctx.has_scalar = scalar is not None
+        ctx.has_h1 = h1 is not None
+        saved = [x, w_down, w_up, b_up, zp, h2]
+        if scalar is not None:
+            saved.append(scalar)
+        if h1 is not None:
+            saved.append(h1)
+        ctx.save_for_backward(*saved)
+        if DEBUG_KEEP_SAVED:
+            LAST_SAVED.update(zp=zp, h2=h2, h1=h1)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        lib = _cabi.load()
+        saved = list(ctx.saved_tensors)
+        x, w_down, w_up, b_up, zp, h2 = saved[:6]
+        rest = saved[6:]
+        scalar = rest.pop(0) if ctx.has_scalar else None
+        h1 = rest.pop(0) if ctx.has_h1 else None
+        n, d = x.shape
+        r = w_down.shape[0]
+        dev = x.device
+        if g_y.stride(-1) != 1 or g_y.stride(0) % 4 != 0 or g_y.data_ptr() % 16 != 0:
+            g_y = g_y.contiguous()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            need_x = ctx.needs_input_grad[0]
+            g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
+            g_wd = torch.empty_like(w_down)
+            g_bd = torch.empty((r,), dtype=torch.float32, device=dev)
+            g_wu = torch.empty_like(w_up)
+            g_bu = torch.empty((d,), dtype=torch.float32, device=dev)
+            g_s = torch.empty((1,), dtype=torch.float32, device=dev) if scalar is not None else None
+            ws = torch.empty(lib.gca_backward_workspace_bytes(n, d, r), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.gca_backward(ctx.graph.handle, g_y.data_ptr(), g_y.stride(0), x.data_ptr(), x.stride(0),
+                                         zp.data_ptr(), _ptr(h1), h2.data_ptr(), w_down.data_ptr(), w_up.data_ptr(),
+                                         b_up.data_ptr(), _ptr(scalar), ctx.act, int(ctx.skip), ws.data_ptr(),
+                                         _ptr(g_x), g_x.stride(0) if need_x else d, g_wd.data_ptr(), g_bd.data_ptr(),
+                                         g_wu.data_ptr(), g_bu.data_ptr(), _ptr(g_s), d, r, stream), "gca_backward")
+        return g_x, g_wd, g_bd, g_wu, g_bu, g_s, None, None, None
+
+
+class _Lin(nn.Module):
+    """Holds ``lin.weight`` [out, in] exactly where PyG's ``GCNConv.lin`` (bias-free Linear) has it."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+
+
+class _GCNConvParams(nn.Module):
+    """Parameter container with the attribute layout of ``torch_geometric.nn.GCNConv`` as the
+    reference touches it (``.lin.weight``, ``.bias``: gconv_adapter.py:73-78).  Construction
+    consumes the RNG like PyG does (glorot on the weight, zeros on the bias)."""
+
+    def __init__(self, in_channels: int, out_channels: int, normalize: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.normalize = in_channels, out_channels, normalize
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        a = math.sqrt(6.0 / (in_channels + out_channels))
+        with torch.no_grad():
+            self.lin.weight.uniform_(-a, a)
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, normalize={self.normalize}"
+
+
+class GConvAdapter(nn.Module):
+    """GConv-Adapter (drop-in for ``src.finetune.gconv_adapter.GConvAdapter``).
+
+    Args:
+        hidden_size (int): Size of the hidden layer.
+        bottleneck_size (int): Size of the bottleneck layer.
+        conv_type (str): Type of graph convolution; only 'gcn' can be constructed ('sage' and
+            'gat' are accepted names in the reference but its constructor fails for them).
+        non_linearity (str): 'relu', 'silu' or 'none'.
+        normalization (str): 'batch_norm', 'layer_norm' or 'none'.
+        learnable_scalar (bool): multiply the output by a learnable scalar.
+        skip_connection (bool): add the input to the output.
+        normalize (bool): add self-loops and use symmetric normalisation coefficients.
+
+    Raises:
+        ValueError: If an invalid conv_type, non_linearity, or normalization is provided.
+    """
+
+    def __init__(self, hidden_size: int, bottleneck_size: int,
+                 conv_type: str = 'gcn', non_linearity: str = 'relu',
+                 normalization: str = 'none', learnable_scalar: bool = False,
+                 skip_connection: bool = True, normalize: bool = True):
+        super().__init__()
+        if conv_type == 'gcn':
+            pass
+        elif conv_type in ('sage', 'gat'):
+            # reference: SAGEConv / GATConv have no `.lin.weight`, so its own constructor raises
+            # AttributeError at gconv_adapter.py:73 (GATConv already rejects `normalize=` at :40).
+            raise AttributeError(f"'{conv_type}' convolutions have no attribute 'lin': the reference "
+                                 "GConvAdapter cannot be constructed with this conv_type either")
+        else:
+            raise ValueError("Invalid conv_type. Supported types: 'gcn', 'sage', 'gat'.")
+        self.conv_down = _GCNConvParams(hidden_size, bottleneck_size, normalize=normalize)
+        self.conv_up = _GCNConvParams(bottleneck_size, hidden_size, normalize=normalize)
+
+        if non_linearity == 'relu':
+            self.act_fn = nn.ReLU()
+        elif non_linearity == 'silu':
+            self.act_fn = nn.SiLU()
+        elif non_linearity == 'none':
+            self.act_fn = nn.Identity()
+        else:
+            raise ValueError("Invalid non_linearity. Supported types: 'relu', 'silu', 'none'.")
+        self._act = _cabi.ACT[non_linearity]
+
+        if normalization == 'batch_norm':
+            self.normalization = nn.BatchNorm1d(hidden_size)
+        elif normalization == 'layer_norm':
+            self.normalization = nn.LayerNorm(hidden_size)
+        elif normalization == 'none':
+            self.normalization = None
+        else:
+            raise ValueError("Invalid normalization. Supported types: 'batch_norm', 'layer_norm', 'none'.")
+
+        if learnable_scalar:
+            self.scalar = nn.Parameter(torch.ones(1))
+        else:
+            self.scalar = None
+
+        self.skip_connection = skip_connection
+        self.normalize = normalize
+        self.hidden_size = hidden_size
+        self.bottleneck_size = bottleneck_size
+
+        torch.nn.init.normal_(self.conv_down.lin.weight, mean=0.0, std=1e-5)
+        torch.nn.init.zeros_(self.conv_down.bias)
+        torch.nn.init.normal_(self.conv_up.lin.weight, mean=0.0, std=1e-5)
+        torch.nn.init.zeros_(self.conv_up.bias)
+
+        # graph structures are shared across adapters / layers / positions through this cache
+        self.graph_cache: GraphCache = GLOBAL_GRAPH_CACHE
+        self.validate_edge_index = True
+
+    # ------------------------------------------------------------------------------
+    def _padded_params(self, d: int, r: int):
+        """Kernels take d % 4 == 0 and r in {8,16,32,64}; other sizes are zero-padded (exact:
+        padded channels carry 0 through bias 0 and relu/silu/identity, and their gradients are
+        dropped by autograd's slice)."""
+        dp = (d + 3) // 4 * 4
+        rp = next((c for c in _FAST_RANKS if c >= r), None)
+        if rp is None:
+            raise RuntimeError(f"gconv_adapter_b200: bottleneck_size {r} > 64 is not supported by the CUDA kernels")
+        wd, bd, wu, bu = self.conv_down.lin.weight, self.conv_down.bias, self.conv_up.lin.weight, self.conv_up.bias
+        if dp != d or rp != r:
+            wd = F.pad(wd, (0, dp - d, 0, rp - r))
+            bd = F.pad(bd, (0, rp - r))
+            wu = F.pad(wu, (0, rp - r, 0, dp - d))
+            bu = F.pad(bu, (0, dp - d))
+        return dp, wd, bd, wu, bu
+
+    def graph_for(self, edge_index: torch.Tensor, num_nodes: int) -> GraphStructure:
+        return self.graph_cache.get(edge_index, num_nodes, self.normalize, validate=self.validate_edge_index)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor = None) -> torch.Tensor:
+        """
+        Args:
+            x: node features ``[N, hidden_size]`` or ``[1, N, hidden_size]`` (fp32, CUDA).
+            edge_index: ``[2, num_edges]`` int64, row 0 = source, row 1 = target.
+            edge_attr: accepted and ignored, as in the reference (gconv_adapter.py:80,92).
+        Returns:
+            A new tensor of the same shape as ``x``.
+        """
+        if not x.is_cuda:
+            raise RuntimeError("gconv_adapter_b200.GConvAdapter runs on CUDA (sm_100a) only; there is no CPU path")
+        if x.dtype != torch.float32:
+            raise RuntimeError("gconv_adapter_b200.GConvAdapter computes in fp32 like the reference; got " + str(x.dtype))
+        if x.dim() == 3:
+            if x.size(0) != 1:
+                raise RuntimeError("3-D input must be [1, N, hidden] (PyG node_dim=-2 semantics with one graph)")
+            x2 = x[0]
+        elif x.dim() == 2:
+            x2 = x
+        else:
+            raise RuntimeError("x must be [N, hidden] or [1, N, hidden]")
+        n, d = x2.shape
+        if d != self.hidden_size:
+            raise RuntimeError(f"expected hidden size {self.hidden_size}, got {d}")
+        dp, wd, bd, wu, bu = self._padded_params(d, self.bottleneck_size)
+        if dp != d:
+            x2 = F.pad(x2, (0, dp - d))
+        if x2.stride(-1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        graph = self.graph_for(edge_index, n)
+        fused_scalar = self.scalar if self.normalization is None else None
+        out = _GConvAdapterFunction.apply(x2, wd, bd, wu, bu, fused_scalar, graph, self._act, self.skip_connection)
+        if dp != d:
+            out = out[:, :d]
+        if x.dim() == 3:
+            out = out.unsqueeze(0)
+
+        # normalisation needs batch / row statistics of the finished sum: stock torch ops,
+        # then the scalar (which is fused into the kernel only when no normalisation sits between)
+        if isinstance(self.normalization, nn.BatchNorm1d):
+            if out.size(0) > 1:
+                out = self.normalization(out)
+        elif isinstance(self.normalization, nn.LayerNorm):
+            out = self.normalization(out)
+        if self.normalization is not None and self.scalar is not None:
+            out = out * self.scalar
+        return out
+
+    def extra_repr(self) -> str:
+        return (f"hidden_size={self.hidden_size}, bottleneck_size={self.bottleneck_size}, "
+                f"skip_connection={self.skip_connection}, normalize={self.normalize}")

@@ -1,0 +1,162 @@
+/*
+ * gca.h -- C ABI of the B200-native GConv-Adapter hot path (libgca.so).
+ *
+ * The reference is pure Python: its "FFI" for this path is the torch.nn.Module
+ *   src/finetune/gconv_adapter.py:5   class GConvAdapter
+ *   src/finetune/gconv_adapter.py:80  forward(x, edge_index, edge_attr=None)
+ * which bottoms out in two torch_geometric GCNConv calls (:40-41, :92) and autograd.
+ * Every entry point below cites the piece of that interface it replaces.  The Python
+ * mirror (gconv_adapter_b200/finetune/gconv_adapter.py) binds them with ctypes; the stub a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says host.
+ *  - every call is asynchronous on `stream` (a cudaStream_t) except where noted; nothing
+ *    is allocated by the library: the caller passes workspaces sized by the *_bytes calls.
+ *  - return value: GCA_OK (0) or a negative gca_status; no exceptions cross the ABI.
+ *  - fp32 row-major tensors; `ld*` is the row pitch in elements (>= d, multiple of 4).
+ *  - node rows are partitioned: a graph handle covers rows [row_begin, row_end) of an
+ *    N-node graph ("local rows", n = row_end - row_begin); neighbour ids stay global.
+ *    A single-GPU run uses row_begin = 0, row_end = N.
+ *
+ * Arithmetic (normalize = 1; dis = (in_degree + 1)^-1/2, A' = A without loops + I):
+ *   P'  = dis * (X Wd^T)                    gca_fwd_project
+ *   Z'  = dis * act(dis * (A' P') + bd)     gca_fwd_hop1          (all-gather P' before)
+ *   H2  = dis * (A' Z')                     gca_fwd_hop2_up       (all-gather Z' before)
+ *   Y   = s * (H2 Wu^T + bu [+ X])
+ * which equals the reference's  s * (Ahat(act(Ahat X Wd^T + bd)) Wu^T + bu + X)  with
+ * Ahat = D^-1/2 A' D^-1/2 applied at width r instead of width d.
+ * normalize = 0: dis = 1, A' = A exactly as given (no loops added or removed).
+ */
+#ifndef GCA_H_
+#define GCA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCA_ABI_VERSION 1
+
+typedef void* gca_stream_t;               /* cudaStream_t */
+typedef struct gca_graph gca_graph;       /* opaque, host-side descriptor of device arrays */
+
+typedef enum gca_status {
+    GCA_OK = 0,
+    GCA_ERR_INVALID_ARG = -1,    /* null pointer, negative size, bad enum */
+    GCA_ERR_WORKSPACE = -2,      /* workspace too small or misaligned (256 B) */
+    GCA_ERR_CUDA = -3,           /* a CUDA runtime call / launch failed (see gca_last_cuda_error) */
+    GCA_ERR_INDEX_RANGE = -4,    /* edge_index holds an id outside [0, N) */
+    GCA_ERR_UNSUPPORTED = -5,    /* shape outside what the kernels implement */
+    GCA_ERR_NO_DEVICE = -6       /* no sm_100 device */
+} gca_status;
+
+typedef enum gca_act { GCA_ACT_NONE = 0, GCA_ACT_RELU = 1, GCA_ACT_SILU = 2 } gca_act;
+
+/* -------- library -------- */
+int         gca_abi_version(void);
+const char* gca_status_string(int status);
+/* cudaGetErrorString of the last CUDA error this library saw on the calling thread (host string). */
+const char* gca_last_cuda_error(void);
+/* 1 if (d, r) is on the vectorised kernels (d % 4 == 0, r in {8,16,32}); 0 = generic kernels. */
+int         gca_shape_is_fast(int32_t d, int32_t r);
+
+/* -------- graph structure (K0) --------
+ * Replaces torch_geometric gcn_norm + add_remaining_self_loops, which the reference
+ * re-runs inside both GCNConv calls of every forward (src/finetune/gconv_adapter.py:92;
+ * PyG default cached=False).  Built once per edge_index and reused by both hops, by the
+ * backward, and by every adapter that sees the same graph.
+ *
+ * src/dst: edge_index[0] / edge_index[1], int64, E entries each (PyG source_to_target).
+ * Produces, for local rows: CSR by target (forward gathers), CSR by source (backward
+ * gathers), neighbour ids ascending inside every row (deterministic sums), and dis.
+ */
+size_t gca_graph_workspace_bytes(int64_t E, int32_t N, int32_t row_begin, int32_t row_end);
+int    gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E, int32_t N,
+                       int32_t row_begin, int32_t row_end, int normalize,
+                       void* workspace, size_t workspace_bytes, gca_stream_t stream,
+                       gca_graph** out);
+/* Synchronises `stream`; returns GCA_ERR_INDEX_RANGE if an id was out of range, else GCA_OK,
+ * and fills nnz / nnz_t (entries of the two CSRs) when the pointers are non-null (host). */
+int    gca_graph_validate(gca_graph* g, gca_stream_t stream, int64_t* nnz, int64_t* nnz_t);
+void   gca_graph_destroy(gca_graph* g);   /* frees the host descriptor only */
+
+typedef struct gca_graph_view {          /* device pointers into the caller's workspace */
+    int32_t  N, row_begin, row_end, normalize;
+    int64_t  capacity;                   /* allocated entries per CSR */
+    const int32_t* rowptr;               /* [n+1]  CSR by target */
+    const int32_t* colidx;               /* [nnz]  source ids, ascending per row */
+    const int32_t* rowptr_t;             /* [n+1]  CSR by source (transpose) */
+    const int32_t* colidx_t;             /* [nnz_t] target ids, ascending per row */
+    const float*   dis;                  /* [n]    (deg+1)^-1/2, or 1 when normalize = 0 */
+} gca_graph_view;
+int    gca_graph_get_view(const gca_graph* g, gca_graph_view* out /* host */);
+/* coef[e] = dis[row(e)] * dis[colidx[e]] for the forward CSR, in CSR order: the fp32
+ * edge weights gcn_norm would produce.  Only valid for a full-graph handle (n == N). */
+int    gca_graph_edge_coef(const gca_graph* g, float* coef, gca_stream_t stream);
+
+/* -------- forward phases (src/finetune/gconv_adapter.py:92-106) --------
+ * n = local rows.  *_full buffers hold all N rows (after the caller's all-gather);
+ * *_local buffers hold the n local rows.  On one GPU they are the same buffer.
+ */
+/* conv_down.lin (d -> r) with the source-side D^-1/2 folded in: P'[i] = dis[i] * X[i] Wd^T */
+int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, const float* Wd /*[r,d]*/,
+                    float* Pp_local /*[n,r]*/, int32_t d, int32_t r, gca_stream_t stream);
+/* conv_down.propagate + bias + act_fn, result pre-scaled for the next hop.
+ * H1_local may be NULL unless act == GCA_ACT_SILU (backward needs the pre-activation). */
+int gca_fwd_hop1(const gca_graph* g, const float* Pp_full /*[N,r]*/, const float* bd /*[r]*/, int act,
+                 float* Zp_local /*[n,r]*/, float* H1_local /*[n,r] or NULL*/, int32_t r,
+                 gca_stream_t stream);
+/* conv_up (propagate at width r, then lin r -> d, + bias) + skip + scalar.
+ * scalar may be NULL (= 1).  H2_local is saved for the backward. */
+int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full /*[N,r]*/, const float* X, int64_t ldx,
+                    const float* Wu /*[d,r]*/, const float* bu /*[d]*/, const float* scalar /*[1] or NULL*/,
+                    int skip, float* H2_local /*[n,r]*/, float* Y, int64_t ldy,
+                    int32_t d, int32_t r, gca_stream_t stream);
+
+/* -------- backward phases (autograd of the above) -------- */
+size_t gca_bwd_scratch_bytes(int32_t d, int32_t r);
+/* gH2'[i] = dis[i] * s * gY[i] Wu ; partial sums for gWu = s * gY^T H2 and gbu = s * sum_i gY[i] */
+int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local,
+               const float* Wu, const float* scalar, float* gH2p_local /*[n,r]*/,
+               void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+/* gH1'[j] = dis[j] * act'(.) * dis[j] * sum_{i in out(j)} gH2'[i] ; partial sums for gbd */
+int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full /*[N,r]*/, const float* Zp_local,
+                 const float* H1_local /*NULL unless silu*/, int act, float* gH1p_local /*[n,r]*/,
+                 void* scratch, int32_t r, gca_stream_t stream);
+/* gP[j] = dis[j] * sum_{i in out(j)} gH1'[i] ; gX = gP Wd [+ s * gY] ; partials for gWd = gP^T X
+ * and for <gY, X> (needed by gscalar).  gX may be NULL (x does not require grad). */
+int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full /*[N,r]*/, const float* X, int64_t ldx,
+                      const float* gY, int64_t ldg, const float* Wd, const float* scalar, int skip,
+                      float* gP_local /*[n,r] workspace*/, float* gX, int64_t ldgx,
+                      void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+/* Deterministic second-stage reduction of the partial sums into the parameter gradients.
+ * Any output pointer may be NULL.  gscalar = <gY, X>(if skip) + <gY^T H2, Wu> + <sum gY, bu>. */
+int gca_bwd_finalize(const void* scratch, const float* Wu, const float* bu, const float* scalar, int skip,
+                     float* gWd /*[r,d]*/, float* gbd /*[r]*/, float* gWu /*[d,r]*/, float* gbu /*[d]*/,
+                     float* gscalar /*[1]*/, int32_t d, int32_t r, gca_stream_t stream);
+
+/* -------- single-GPU conveniences: the whole forward / backward on one stream -------- */
+size_t gca_forward_workspace_bytes(int32_t n, int32_t d, int32_t r);   /* P' scratch */
+int gca_forward(const gca_graph* g, const float* X, int64_t ldx,
+                const float* Wd, const float* bd, const float* Wu, const float* bu, const float* scalar,
+                int act, int skip, void* workspace,
+                float* Zp_save, float* H1_save /*NULL unless silu*/, float* H2_save,
+                float* Y, int64_t ldy, int32_t d, int32_t r, gca_stream_t stream);
+size_t gca_backward_workspace_bytes(int32_t n, int32_t d, int32_t r);  /* gH2', gH1', gP + scratch */
+int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, const float* X, int64_t ldx,
+                 const float* Zp_save, const float* H1_save, const float* H2_save,
+                 const float* Wd, const float* Wu, const float* bu, const float* scalar,
+                 int act, int skip, void* workspace,
+                 float* gX, int64_t ldgx, float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar,
+                 int32_t d, int32_t r, gca_stream_t stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t gca_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCA_H_ */
