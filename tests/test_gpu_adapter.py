@@ -55,12 +55,13 @@ def run_oracle(x, ei, params, g_out, mask=None, **kw):
     return y.detach(), grads, m
 
 
-def compare(ours, ref, tag):
+def compare(ours, ref, tag, g_out=None, batchnorm=False):
     y, g, _ = ours
     yr, gr, _ = ref
     assert_close(y, yr, f"{tag}: y")
     for k in gr:
-        assert_close(g[k], gr[k], f"{tag}: grad {k}")
+        floor = 1e-6 * float(g_out.abs().sum(0).max()) if (batchnorm and k == "conv_up.bias") else 0.0
+        assert_close(g[k], gr[k], f"{tag}: grad {k}", noise_floor=floor)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -74,7 +75,10 @@ def test_golden_vectors(name):
     assert_close(y, g["y"], name + ": y")
     assert_close(grads["x"], g["g_x"], name + ": g_x")
     for k in params:
-        assert_close(grads[k], g["grad." + k], f"{name}: grad {k}")
+        # BatchNorm removes the column mean, so d loss / d conv_up.bias is exactly 0 in real arithmetic:
+        # both sides hold only cancellation noise of sum_i |g_out[i]| * eps.
+        floor = 1e-6 * float(np.abs(g["g_out"]).sum(0).max()) if (name == "mid_batchnorm" and k == "conv_up.bias") else 0.0
+        assert_close(grads[k], g["grad." + k], f"{name}: grad {k}", noise_floor=floor)
 
 
 def test_golden_cora_shaped_config0():
@@ -109,7 +113,7 @@ def _oracle_parity(ei, n, d, r, seed, tag, three_d=False, **over):
         assert diff.sum().item() <= 1e-5 * mask.numel() + 2
         if diff.any():
             assert h1[diff].abs().max().item() <= 1e-5 * h1.abs().max().item()
-    compare(ours, ref, tag)
+    compare(ours, ref, tag, g_out=g_out, batchnorm=kw["normalization"] == "batch_norm")
     return ours, ref
 
 
@@ -201,7 +205,8 @@ def test_bitwise_determinism_and_graph_cache_reuse():
     m = a[2]
     eic = ei.cuda()
     m(x.cuda(), eic); m(x.cuda(), eic)
-    assert m.graph_cache.misses == 1 and m.graph_cache.hits == 1
+    # run_ours built the structure once for its own device copy of edge_index; eic is a new tensor
+    assert m.graph_cache.misses == 2 and m.graph_cache.hits == 1
 
 
 @pytest.mark.parametrize("name,r", [("arxiv", 16), ("products", 32)])

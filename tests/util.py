@@ -32,7 +32,10 @@ def ctor_kwargs(cfg: dict) -> dict:
     return {k: v for k, v in cfg.items() if k != "three_d"}
 
 
-def assert_close(ours, ref, what: str, rtol: float = RTOL, atol_scale: float = ATOL_SCALE, max_outlier_frac: float = 0.0):
+def assert_close(ours, ref, what: str, rtol: float = RTOL, atol_scale: float = ATOL_SCALE, max_outlier_frac: float = 0.0,
+                 noise_floor: float = 0.0):
+    """|ours - ref| <= atol_scale * max|ref| + rtol * |ref| (+ noise_floor, for quantities that are
+    mathematically zero so that the reference itself holds only rounding noise)."""
     ours = torch.as_tensor(ours).detach().double().cpu().reshape(-1)
     ref = torch.as_tensor(ref).detach().double().cpu().reshape(-1)
     assert ours.shape == ref.shape, f"{what}: shape {tuple(ours.shape)} vs {tuple(ref.shape)}"
@@ -40,7 +43,7 @@ def assert_close(ours, ref, what: str, rtol: float = RTOL, atol_scale: float = A
     if ref.numel() == 0:
         return
     scale = ref.abs().max().item()
-    tol = atol_scale * scale + rtol * ref.abs()
+    tol = atol_scale * scale + rtol * ref.abs() + noise_floor
     bad = (ours - ref).abs() > tol
     nbad = int(bad.sum())
     allowed = int(max_outlier_frac * ref.numel())
