@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py - GConv-Adapter forward + backward throughput (edges/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload arxiv|products|pubmed|cora|molecules]
+    python bench.py --impl reference ...        # the CPU oracle timed on the host cores
+
+A step = one adapter forward + backward over the workload graph.  Default workload (N = 1) is
+BASELINE.json configs[3], the ogbn-arxiv-shaped graph the metric is quoted on (169,343 nodes,
+1,166,243 edges, hidden 256, rank 16), synthetic data, random weights.  For N > 1 the node rows are
+partitioned over the ranks and the r-wide activations are all-gathered (strong scaling).
+
+Prints ONE JSON line (rank 0) with the keys of the driver contract plus `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches`, `phases` and `step_roofline`.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "gconv_adapter_fwd_bwd_edges_per_sec"
+UNIT = "edges/s"
+
+
+# ---------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="arxiv (default) | products | pubmed | cora | molecules")
+    ap.add_argument("--power-law", action="store_true", help="hub-heavy degree distribution instead of uniform")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from gconv_adapter_b200.graphs.synthetic import SHAPES, make_graph
+    name = args.workload or "arxiv"
+    ei, n = make_graph(name, seed=0, power_law=args.power_law)
+    s = SHAPES[name]
+    return name, ei, n, s.hidden, s.rank
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n, e_prime, d, r):
+    """Minimal HBM bytes per launch of each kernel and of the whole fwd+bwd (DESIGN.md section 5;
+    SURVEY.md section 8d: A_min = 28 N d + 52 N r + 16 E' + 32 N)."""
+    nd, nr = 4 * n * d, 4 * n * r
+    idx = 4 * e_prime + 4 * n          # colidx + rowptr
+    dis = 4 * n
+    per = {
+        "project_fwd": nd + nr + dis,                 # X -> P'
+        "hop_fwd": 2 * nr + idx + dis,                # P' -> Z'
+        "hop_expand_fwd": 2 * nr + idx + dis + 2 * nd,  # Z' -> H2 ; X -> Y
+        "project_bwd": nd + nr + dis,                 # gY -> gH2'
+        "wgrad_up": nd + nr,                          # gY, H2 -> gWu partials
+        "hop_bwd": 3 * nr + idx + dis,                # gH2', Z' -> gH1'
+        "hop_expand_bwd": 2 * nr + idx + dis + 2 * nd,  # gH1' -> gP ; gY -> gX
+        "wgrad_down": 2 * nd + nr,                    # X, gY(dot), gP -> gWd partials
+        "finalize": 0,
+    }
+    total = 28 * n * d + 52 * n * r + 16 * e_prime + 32 * n
+    return per, total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step_seconds(ei, n, d, r, params, x, g_out, steps, warmup, threads=None):
+    """CPU baseline: the restated reference module (oracle/pyg_restated.py), fwd + bwd, fp32."""
+    from oracle.pyg_restated import GConvAdapterRef
+    if threads:
+        torch.set_num_threads(threads)
+    m = GConvAdapterRef(d, r, learnable_scalar=True)
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k, v in params.items():
+            sd[k].copy_(v)
+    times = []
+    for it in range(warmup + steps):
+        for p in m.parameters():
+            p.grad = None
+        xx = x.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        y = m(xx, ei)
+        y.backward(g_out)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    return times
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gconv_adapter_b200.graphs.synthetic import make_inputs
+    name, ei, n, d, r = workload(args)
+    x, g_out, params = make_inputs(n, d, r, seed=0)
+    cores = os.cpu_count() or 1
+    times = oracle_step_seconds(ei, n, d, r, params, x, g_out, args.steps, args.warmup, threads=cores)
+    e = ei.size(1)
+    total = sum(times)
+    val = e * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}-shaped: N={n} E={e} hidden={d} rank={r}", "inputs": "host memory (CPU run)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"full {name}-shaped fwd+bwd x {len(times)} steps; restated PyG GCNConv op sequence "
+                                   f"(torch-geometric is not installable here), {cpu_model()}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from gconv_adapter_b200.partition_bench import run_partitioned   # multi-GPU leg
+        return run_partitioned(args, METRIC, UNIT)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU oracle)")
+    from gconv_adapter_b200 import GConvAdapter, GraphCache, _cabi
+    from gconv_adapter_b200.graphs.synthetic import make_inputs
+    lib = _cabi.load()
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    name, ei, n, d, r = workload(args)
+    e = ei.size(1)
+    x, g_out, params = make_inputs(n, d, r, seed=0)
+    m = GConvAdapter(d, r, learnable_scalar=True)
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k, v in params.items():
+            sd[k].copy_(v)
+    m = m.to(dev)
+    m.graph_cache = GraphCache()
+    eid = ei.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    gd = g_out.to(dev)
+    graph = m.graph_for(eid, n)                 # built once; the timed steps reuse it (static graph)
+    e_prime = graph.nnz
+
+    def step():
+        xd.grad = None
+        for p in m.parameters():
+            p.grad = None
+        y = m(xd, eid)
+        y.backward(gd)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = lib.gca_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms_step = t0.elapsed_time(t1) / args.steps
+    launches = lib.gca_launch_count() - l0
+    clocks = sampler.stop()
+
+    # ---- per-kernel device times (CUDA events on the launching stream, inside libgca) ----
+    lib.gca_profile_enable(1)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.gca_profile_report(buf, len(buf))
+    lib.gca_profile_enable(0)
+    prof = json.loads(buf.value.decode())
+    per_bytes, a_min = algorithmic_bytes(n, e_prime, d, r)
+    peak, peak_src = peaks()
+    phases = {}
+    for k, v in prof.items():
+        avg_ms = v["ms"] / max(v["launches"], 1)
+        b = per_bytes.get(k, 0)
+        phases[k] = {"ms": round(avg_ms, 5), "launches_per_step": v["launches"] / args.steps,
+                     "alg_MB": round(b / 1e6, 2), "GBs": round(b / 1e6 / avg_ms, 1) if avg_ms > 0 else None}
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
+    achieved = per_bytes.get(dom, 0) / 1e6 / dom_ms
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")     # per-launch dram bytes from the ncu --set full capture
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(name, {}).get(dom)
+        except Exception:
+            traffic = None
+    kernel_ms = sum(v["ms"] for v in prof.values()) / args.steps
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": per_bytes.get(dom, 0), "ms_per_launch": round(dom_ms, 5),
+                "share_of_step": round(prof[dom]["ms"] / args.steps / kernel_ms, 3)}
+    step_gbs = a_min / 1e6 / ms_step
+    step_roofline = {"alg_bytes_per_step": a_min, "achieved": round(step_gbs, 1), "unit": "GB/s",
+                     "frac_of_measured_peak": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4),
+                     "sum_of_kernel_ms": round(kernel_ms, 5)}
+
+    # ---- e2e: host inputs, H2D + fwd + bwd + D2H of the loss, through the nn.Module ----
+    e2e = None
+    if not args.no_e2e:
+        x_host = x.pin_memory()
+        x_dev = torch.empty_like(xd)
+
+        def e2e_step():
+            for p in m.parameters():
+                p.grad = None
+            x_dev.copy_(x_host, non_blocking=True)
+            xin = x_dev.detach().requires_grad_(True)
+            y = m(xin, eid)
+            loss = (y * gd).sum()
+            loss.backward()
+            return loss.item()
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        k2 = max(5, args.steps // 3)
+        c0 = time.perf_counter()
+        t0.record()
+        for _ in range(k2):
+            e2e_step()
+        t1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - c0) / k2
+        dev_s = t0.elapsed_time(t1) / 1e3 / k2
+        e2e = {"value": e / max(wall, dev_s), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+               "d2h_bytes_per_step": 4, "ms_per_step": round(1e3 * max(wall, dev_s), 4), "steps": k2}
+
+    # ---- CPU baseline (bounded: the oracle at full size takes seconds per step) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        ksteps = 3 if n > 50_000 else 10
+        times = oracle_step_seconds(ei, n, d, r, params, x, g_out, ksteps, 1)
+        cpu = {"value": e * len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"full {name}-shaped fwd+bwd, {len(times)} steps after 1 warm-up, {cpu_model()}",
+               "ms_per_step": round(1e3 * sum(times) / len(times), 2)}
+
+    line = {
+        "metric": METRIC, "value": e / (ms_step / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}-shaped: N={n} E={e} (E'={e_prime} with self loops) hidden={d} rank={r}"
+                               + (" power-law" if args.power_law else ""),
+                   "adapter": "relu, skip, learnable scalar, normalize=True", "graph": "static, structure cached",
+                   "l2": "inputs larger than L2 (X, gY, Y, gX are %d MB each)" % (4 * n * d // 1_000_000)
+                         if 4 * n * d > 126e6 else "working set fits L2; no flush (latency-bound config)",
+                   "parallelism": "1 GPU"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "step_roofline": step_roofline, "phases": phases, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "gca_backward": (C.c_int, [_f, _f, _i64, _f, _i64, _f, _f, _f, _f, _f, _f, _f, C.c_int, C.c_int, _f,
                                _f, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f]),
     "gca_launch_count": (_i64, []),
+    "gca_profile_enable": (C.c_int, [C.c_int]),
+    "gca_profile_report": (C.c_int, [C.c_char_p, _sz]),
 }
 
 _lib = None

@@ -28,6 +28,18 @@ extern thread_local cudaError_t tl_last_cuda_error;
 void count_launch(int n = 1);
 int num_sms();
 
+// Optional per-kernel timing with CUDA events recorded on the launching stream
+// (gca_profile_enable / gca_profile_report); off by default and free when off.
+bool prof_enabled();
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(const char* name, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_begin(name, s); }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+
 inline int record(cudaError_t e) {
     if (e != cudaSuccess) { tl_last_cuda_error = e; return GCA_ERR_CUDA; }
     return GCA_OK;

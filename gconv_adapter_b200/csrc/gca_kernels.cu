@@ -540,7 +540,10 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
     GCA_TRY(set_smem(k_project<R, W_IS_RD>, smem));
     const int ntiles = (n + TILE - 1) / TILE;
     const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
-    k_project<R, W_IS_RD><<<grid, 256, smem, st>>>(A, lda, W, rowscale, scalar, out, n, d);
+    {
+        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
+        k_project<R, W_IS_RD><<<grid, 256, smem, st>>>(A, lda, W, rowscale, scalar, out, n, d);
+    }
     GCA_LAUNCH_OK();
     return GCA_OK;
 }
@@ -553,7 +556,10 @@ int launch_hop(const int* rowptr, const int* colidx, const float* dis, const flo
     const int cap = BWD ? (kMaxPartsBd < 8 * num_sms() ? kMaxPartsBd : 8 * num_sms()) : 8 * num_sms();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    k_hop<R, BWD><<<grid, 256, 0, st>>>(rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n);
+    {
+        ProfScope ps(BWD ? "hop_bwd" : "hop_fwd", st);
+        k_hop<R, BWD><<<grid, 256, 0, st>>>(rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n);
+    }
     GCA_LAUNCH_OK();
     return GCA_OK;
 }
@@ -568,8 +574,11 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
     GCA_TRY(set_smem(k_hop_expand<R, W_IS_DR>, smem));
     const int ntiles = (n + kTileRows - 1) / kTileRows;
     const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
-    k_hop_expand<R, W_IS_DR><<<grid, 256, smem, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
-                                                       alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+    {
+        ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+        k_hop_expand<R, W_IS_DR><<<grid, 256, smem, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
+                                                           alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+    }
     GCA_LAUNCH_OK();
     return GCA_OK;
 }
@@ -595,8 +604,11 @@ int launch_wgrad(const float* A, int64_t lda, const float* H, const float* B, in
         const size_t smem = smem_h > smem_g ? smem_h : smem_g;
         if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
         GCA_TRY(set_smem(k_wgrad<R>, smem));
-        k_wgrad<R><<<grid, warps * 32, smem, st>>>(A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d,
-                                                    col0, dsub, nchunks, RS);
+        {
+            ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st);
+            k_wgrad<R><<<grid, warps * 32, smem, st>>>(A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d,
+                                                        col0, dsub, nchunks, RS);
+        }
         GCA_LAUNCH_OK();
     }
     return GCA_OK;
@@ -737,8 +749,11 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
     const Scratch S = scratch_ptrs(const_cast<void*>(scratch), d, r);
     int grid = (r * d + 255) / 256;
     if (grid > kMaxFin) grid = kMaxFin;
-    k_finalize<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S.gu, S.col, S.gd, S.dot, S.bd, S.gsp, S.header, Wu, bu,
-                                                                     scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r);
+    {
+        ProfScope ps("finalize", static_cast<cudaStream_t>(stream));
+        k_finalize<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S.gu, S.col, S.gd, S.dot, S.bd, S.gsp, S.header, Wu, bu,
+                                                                         scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r);
+    }
     GCA_LAUNCH_OK();
     return GCA_OK;
 }

@@ -1,5 +1,11 @@
 // Library-level entry points of libgca: version, status strings, device probe, launch counter.
 #include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "gca_common.cuh"
 
@@ -19,7 +25,60 @@ int num_sms() {
     return cached;
 }
 
+struct ProfEntry { const char* name; cudaEvent_t a, b; };
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfEntry> g_prof;
+
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void prof_begin(const char* name, cudaStream_t st) {
+    ProfEntry e{name, nullptr, nullptr};
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(e);
+}
+void prof_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof.empty() && g_prof.back().b) cudaEventRecord(g_prof.back().b, st);
+}
+
 }  // namespace gca
+
+extern "C" int gca_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(gca::g_prof_mu);
+    for (auto& e : gca::g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    gca::g_prof.clear();
+    gca::g_prof_on.store(on != 0);
+    return GCA_OK;
+}
+
+// Synchronises the recorded events and writes {"name": {"launches": n, "ms": total}, ...} (JSON).
+extern "C" int gca_profile_report(char* buf, size_t n) {
+    if (!buf || n == 0) return GCA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(gca::g_prof_mu);
+    std::map<std::string, std::pair<long, double>> acc;
+    std::vector<std::string> order;
+    for (auto& e : gca::g_prof) {
+        if (cudaEventSynchronize(e.b) != cudaSuccess) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) continue;
+        auto it = acc.find(e.name);
+        if (it == acc.end()) { order.push_back(e.name); acc[e.name] = {1, ms}; }
+        else { it->second.first++; it->second.second += ms; }
+    }
+    std::string out = "{";
+    for (size_t i = 0; i < order.size(); ++i) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", i ? ", " : "", order[i].c_str(),
+                 acc[order[i]].first, acc[order[i]].second);
+        out += tmp;
+    }
+    out += "}";
+    if (out.size() + 1 > n) return GCA_ERR_WORKSPACE;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return GCA_OK;
+}
 
 extern "C" int gca_abi_version(void) { return GCA_ABI_VERSION; }
 

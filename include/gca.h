@@ -155,6 +155,11 @@ int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, const float* 
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t gca_launch_count(void);
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch is bracketed by
+ * cudaEvents on its own stream.  enable(0|1) also clears what was recorded.  report synchronises
+ * and writes JSON {"kernel": {"launches": n, "ms": total}, ...} into buf (host). */
+int gca_profile_enable(int on);
+int gca_profile_report(char* buf, size_t buf_bytes);
 
 #ifdef __cplusplus
 }
