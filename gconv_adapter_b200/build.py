@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = ["gca_lib.cu", "gca_graph.cu", "gca_kernels.cu"]
+SOURCES = ["gca_lib.cu", "gca_graph.cu", "gca_kernels.cu", "gca_tc_project.cu"]
 OUT = os.path.join(HERE, "lib", "libgca.so")
 
 

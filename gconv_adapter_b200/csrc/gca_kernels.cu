@@ -14,6 +14,13 @@
 #include "gca_common.cuh"
 
 namespace gca {
+
+// tensor-core (tcgen05) variants live in gca_tc_*.cu; they return GCA_ERR_UNSUPPORTED for shapes
+// they do not cover and the CUDA-core kernels below take over.
+int launch_project_tc(int r, bool w_is_rd, const float* A, int64_t lda, const float* W, const float* rowscale,
+                      const float* scalar, float* out, int n, int d, cudaStream_t st);
+bool tc_enabled();
+
 namespace {
 
 constexpr int kLongRow = 96;
@@ -459,8 +466,26 @@ k_wgrad(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, c
 }
 
 // ------------------------------------------------------------------------------------------
-// K6: sum the partials in index order; the last CTA to finish adds up the gscalar pieces.
+// K6: second-stage reduction of the per-CTA partials, fixed order.  A warp owns 4 column quads
+// (16 consecutive outputs); its 8 lanes per quad each sum every 8th partial, then a 3-step
+// butterfly adds the 8 lane sums.  The last CTA to finish adds up the gscalar pieces.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 sum_partials(const float* __restrict__ part, int np, size_t pitch, int idx4, int pl) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = pl;
+    for (; p + 24 < np; p += 32) {
+        const float4 v0 = ldg4(part + (size_t)p * pitch + idx4 * 4);
+        const float4 v1 = ldg4(part + (size_t)(p + 8) * pitch + idx4 * 4);
+        const float4 v2 = ldg4(part + (size_t)(p + 16) * pitch + idx4 * 4);
+        const float4 v3 = ldg4(part + (size_t)(p + 24) * pitch + idx4 * 4);
+        acc = f4_add(acc, v0); acc = f4_add(acc, v1); acc = f4_add(acc, v2); acc = f4_add(acc, v3);
+    }
+    for (; p < np; p += 8) acc = f4_add(acc, ldg4(part + (size_t)p * pitch + idx4 * 4));
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
+    return acc;
+}
+
 __global__ void __launch_bounds__(256)
 k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, const float* __restrict__ partGd,
            const float* __restrict__ partDot, const float* __restrict__ partBd, float* gsp, int* header,
@@ -468,29 +493,48 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
            float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar, int d, int r) {
     const int pu = header[0], pd = header[1], pb = header[2];
     const float s = scalar ? __ldg(scalar) : 1.f;
-    const int rd = r * d;
+    const int rd4 = (r * d) >> 2, d4 = d >> 2, r4 = r >> 2;
+    const int lane = threadIdx.x & 31;
+    const int pl = lane & 7;                       // partial lane
+    const int wq = lane >> 3;                      // which of the warp's 4 quads
+    const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wtotal = gridDim.x * (blockDim.x >> 5);
     float gs = 0.f;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rd; idx += gridDim.x * blockDim.x) {
-        const int c = idx / d, k = idx - c * d;
-        float gu = 0.f;
-        for (int p = 0; p < pu; ++p) gu += partGu[(size_t)p * rd + idx];
-        if (gWu) gWu[(size_t)k * r + c] = s * gu;
-        gs = fmaf(gu, __ldg(Wu + (size_t)k * r + c), gs);
-        if (gWd) {
-            float gd = 0.f;
-            for (int p = 0; p < pd; ++p) gd += partGd[(size_t)p * rd + idx];
-            gWd[idx] = gd;
+    for (int base = wglobal * 4; base < rd4; base += wtotal * 4) {       // warp-uniform trip count
+        const int idx4 = base + wq;
+        const bool ok = idx4 < rd4;
+        const int q = ok ? idx4 : rd4 - 1;
+        const float4 gu = sum_partials(partGu, pu, (size_t)r * d, q, pl);
+        float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gWd) gd = sum_partials(partGd, pd, (size_t)r * d, q, pl);
+        if (ok && pl == 0) {
+            const int c = (q * 4) / d, k = q * 4 - c * d;
+            const float g4[4] = {gu.x, gu.y, gu.z, gu.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (gWu) gWu[(size_t)(k + j) * r + c] = s * g4[j];
+                gs = fmaf(g4[j], __ldg(Wu + (size_t)(k + j) * r + c), gs);
+            }
+            if (gWd) *reinterpret_cast<float4*>(gWd + (size_t)q * 4) = gd;
         }
-        if (idx < d) {
-            float cs = 0.f;
-            for (int p = 0; p < pu; ++p) cs += partCol[(size_t)p * d + idx];
-            if (gbu) gbu[idx] = s * cs;
-            gs = fmaf(cs, __ldg(bu + idx), gs);
+    }
+    for (int base = wglobal * 4; base < d4; base += wtotal * 4) {
+        const int idx4 = base + wq;
+        const bool ok = idx4 < d4;
+        const int q = ok ? idx4 : d4 - 1;
+        const float4 cs = sum_partials(partCol, pu, (size_t)d, q, pl);
+        if (ok && pl == 0) {
+            if (gbu) *reinterpret_cast<float4*>(gbu + q * 4) = f4_scale(cs, s);
+            const float4 b = ldg4(bu + q * 4);
+            gs = fmaf(cs.x, b.x, fmaf(cs.y, b.y, fmaf(cs.z, b.z, fmaf(cs.w, b.w, gs))));
         }
-        if (idx < r && gbd) {
-            float t = 0.f;
-            for (int p = 0; p < pb; ++p) t += partBd[(size_t)p * r + idx];
-            gbd[idx] = t;
+    }
+    if (gbd) {
+        for (int base = wglobal * 4; base < r4; base += wtotal * 4) {
+            const int idx4 = base + wq;
+            const bool ok = idx4 < r4;
+            const int q = ok ? idx4 : r4 - 1;
+            const float4 t = sum_partials(partBd, pb, (size_t)r, q, pl);
+            if (ok && pl == 0) *reinterpret_cast<float4*>(gbd + q * 4) = t;
         }
     }
     if (!gscalar) return;
@@ -534,6 +578,10 @@ template <int R, bool W_IS_RD>
 int launch_project(const float* A, int64_t lda, const float* W, const float* rowscale, const float* scalar,
                    float* out, int n, int d, cudaStream_t st) {
     if (n == 0) return GCA_OK;
+    if (tc_enabled()) {
+        const int st_tc = launch_project_tc(R, W_IS_RD, A, lda, W, rowscale, scalar, out, n, d, st);
+        if (st_tc != GCA_ERR_UNSUPPORTED) return st_tc;
+    }
     constexpr int TILE = 32 * (64 / R);
     const size_t smem = sizeof(float) * (size_t)(d / 4) * (4 * R + 4);
     if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
@@ -747,7 +795,8 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
                                 gca_stream_t stream) {
     if (!scratch || !Wu || !bu || d <= 0 || r <= 0) return GCA_ERR_INVALID_ARG;
     const Scratch S = scratch_ptrs(const_cast<void*>(scratch), d, r);
-    int grid = (r * d + 255) / 256;
+    int grid = ((r * d) / 16 + 7) / 8;               // one warp per 16 outputs, 8 warps per CTA
+    if (grid < 1) grid = 1;
     if (grid > kMaxFin) grid = kMaxFin;
     {
         ProfScope ps("finalize", static_cast<cudaStream_t>(stream));

@@ -1,6 +1,7 @@
 // Library-level entry points of libgca: version, status strings, device probe, launch counter.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -23,6 +24,16 @@ int num_sms() {
         sms = 148;   // B200
     cached = sms;
     return cached;
+}
+
+// GCA_DISABLE_TC=1 forces the CUDA-core kernels (A/B runs, debugging).
+bool tc_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GCA_DISABLE_TC");
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1;
 }
 
 struct ProfEntry { const char* name; cudaEvent_t a, b; };
