@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-I" + os.path.join(ROOT, "include"), "--shared", "-Xcompiler", "-fPIC", "-o", OUT]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("GCA_EXTRA_NVCC_FLAGS", "").split()
     cmd += [os.path.join(HERE, "csrc", s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

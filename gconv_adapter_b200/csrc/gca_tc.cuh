@@ -101,9 +101,16 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// x = hi + lo (+ <= 2^-22 |x|): hi = x with the 13 low mantissa bits cleared (exactly representable in
+// tf32; the truncation error is carried exactly by x - hi), lo = (x - hi) rounded to nearest tf32 so the
+// representation error stays unbiased.  One LOP + FADD + IADD + LOP per value (cvt.rna.tf32.f32 compiles to
+// a 4-instruction sequence with an inf/nan test).
+__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float4 x, float4& hi, float4& lo) {
-    hi = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
-    lo = make_float4(to_tf32(x.x - hi.x), to_tf32(x.y - hi.y), to_tf32(x.z - hi.z), to_tf32(x.w - hi.w));
+    split1(x.x, hi.x, lo.x); split1(x.y, hi.y, lo.y); split1(x.z, hi.z, lo.z); split1(x.w, hi.w, lo.w);
 }
 
 // Byte offset of element (row, col) in a column-chunk-major core-matrix tile with `rows` rows.

@@ -1,13 +1,13 @@
 // K1-tc: out[i, 0:R] = rowscale[i] * s * sum_k A[i,k] W[k, 0:R]  on tcgen05 (3xTF32, fp32 TMEM accumulators).
 //
-// Persistent, warp-specialised CTA (one per SM, 13 warps):
-//   warps 0-7   producers : LDG.128 a [128 rows x 64 cols] chunk of A (4 rows x 128 B per warp instruction,
-//                           two chunks in flight per thread), split every value into tf32 hi / lo,
+// Persistent, warp-specialised CTA (one per SM, 21 warps):
+//   warps 0-15  producers : LDG.128 a [128 rows x 64 cols] chunk of A (4 rows x 128 B per warp instruction,
+//                           four independent groups of 4 warps), split every value into tf32 hi / lo,
 //                           STS both into a pipeline stage
-//   warp  12    MMA issuer: per K-step (8 columns)  A_hi x [W_hi | W_lo]  (M=128, N=2R)  and
+//   warp  20    MMA issuer: per K-step (8 columns)  A_hi x [W_hi | W_lo]  (M=128, N=2R)  and
 //                           A_lo x W_hi (N=R): every A byte is read from shared memory once;
 //                           tcgen05.commit frees the stage / publishes the accumulators
-//   warps 8-11  epilogue  : tcgen05.ld the accumulators (lane = row), add, scale, STG.128
+//   warps 16-19 epilogue  : tcgen05.ld the accumulators (lane = row), add, scale, STG.128
 // Stages and accumulators are handed over with mbarriers; accumulators are double-buffered in TMEM
 // so the epilogue of tile t overlaps the loads and MMAs of tile t+1.
 //
@@ -22,6 +22,17 @@
 namespace gca {
 namespace tc {
 
+#ifdef GCA_TC_DEBUG
+// cycles summed over CTAs: [0] producer wait-empty, [1] producer wait-data+split+STS, [2] producer total,
+// [3] MMA wait-full, [4] MMA issue, [5] MMA wait-tempty, [6] epilogue wait-tfull, [7] epilogue rest, [8] kernel total (warp 0)
+__device__ unsigned long long g_dbg[16];
+#define DBG_T(var) const long long var = clock64()
+#define DBG_ADD(slot, expr) dbg_acc[slot] += (expr)
+#else
+#define DBG_T(var)
+#define DBG_ADD(slot, expr)
+#endif
+
 constexpr int kRows = 128;                 // rows per tile  (UMMA M)
 constexpr int kCols = 64;                  // columns per pipeline stage
 // S_C: bytes between 4-column chunks.  Padded by 16 B so that the 8 lanes of a quarter warp, which hold
@@ -30,9 +41,9 @@ constexpr int kCols = 64;                  // columns per pipeline stage
 constexpr int kColChunk = (kRows / 8) * 128 + 16;
 constexpr int kHalfBytes = (kCols / 4) * kColChunk;   // ~32 KB: hi part of a stage; lo part follows
 constexpr int kStageBytes = 2 * kHalfBytes;           // ~64 KB
-constexpr int kProdWarps = 8;
+constexpr int kProdWarps = 16;
 constexpr int kThreads = 32 * (kProdWarps + 4 + 1);
-constexpr int kPerThread = (kRows * kCols / 4) / (32 * kProdWarps);   // float4 per producer thread per chunk (8)
+constexpr int kPerThread = (kRows * kCols / 4) / 128;   // float4 per producer thread per chunk (16)
 
 template <int R, bool W_IS_RD>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -57,10 +68,14 @@ k_project_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * nstage + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef GCA_TC_DEBUG
+    long long dbg_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long dbg_t0 = clock64();
+#endif
 
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(full_bar(s), kProdWarps); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         fence_barrier_init();
     }
@@ -87,26 +102,39 @@ k_project_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
 
     if (warp < kProdWarps) {
         // ================= producers =================
+        // Group g (4 warps) owns ring stage g for the whole kernel and fills chunks g, g + nstage, ...: one
+        // producer per stage keeps the mbarrier phases in lock step (a parity wait cannot tell "two uses
+        // ago" from "now").  A thread never has loads of a later chunk in flight when it executes
+        // fence.proxy.async (which waits for the thread's outstanding memory operations); the other groups
+        // keep HBM busy meanwhile.
         const int k4i = lane & 7, ri = lane >> 3;          // 8 lanes = one 128-byte line of a row
-        const int total = my_tiles * nchunks;
-        auto load = [&](float4 (&v)[kPerThread], int it) {
-            const int tile = blockIdx.x + (it / nchunks) * gridDim.x, ch = it % nchunks;
+        const int grp = warp >> 2, wq = warp & 3;
+        const int total = grp < nstage ? my_tiles * nchunks : 0;
+        const int kGroups = nstage;
+        int ltile = blockIdx.x, lch = grp;                 // (tile, chunk) of this group's next item
+        while (lch >= nchunks) { lch -= nchunks; ltile += gridDim.x; }
+        const int ps = grp;                                // this group's stage
+        int pq = 0;                                        // how many times it has been filled
+        for (int it = grp; it < total; it += kGroups) {
+            float4 v[kPerThread];
+            DBG_T(l0);
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) {
-                // j -> (column half jc, row quad jr): rows warp*16 + jr*4 + ri, column quads jc*8 + k4i
+                // j -> (column half jc, row quad jr): rows wq*32 + jr*4 + ri, column quads jc*8 + k4i
                 const int jc = j & 1, jr = j >> 1;
-                const int row = min(tile * kRows + warp * 16 + jr * 4 + ri, n - 1);
-                v[j] = ldg4_stream(A + (size_t)row * lda + ch * kCols + jc * 32 + k4i * 4);
+                const int row = min(ltile * kRows + wq * 32 + jr * 4 + ri, n - 1);
+                v[j] = ldg4_stream(A + (size_t)row * lda + lch * kCols + jc * 32 + k4i * 4);
             }
-        };
-        auto store = [&](const float4 (&v)[kPerThread], int it) {
-            const int s = it % nstage;
-            mbar_wait(empty_bar(s), (uint32_t)(((it / nstage) & 1) ^ 1));
-            uint8_t* st = stages + (size_t)s * kStageBytes;
+            DBG_T(w0);
+            DBG_ADD(2, w0 - l0);
+            mbar_wait(empty_bar(ps), (uint32_t)((pq & 1) ^ 1));
+            DBG_T(w1);
+            DBG_ADD(0, w1 - w0);
+            uint8_t* st = stages + (size_t)ps * kStageBytes;
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) {
                 const int jc = j & 1, jr = j >> 1;
-                const int rl = warp * 16 + jr * 4 + ri;            // row inside the tile
+                const int rl = wq * 32 + jr * 4 + ri;              // row inside the tile
                 const uint32_t off = (uint32_t)((jc * 8 + k4i) * kColChunk + (rl >> 3) * 128 + (rl & 7) * 16);
                 float4 hi, lo;
                 split_tf32(v[j], hi, lo);
@@ -115,60 +143,71 @@ k_project_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
-        };
-        float4 va[kPerThread], vb[kPerThread];
-        if (total > 0) load(va, 0);
-        for (int it = 0; it < total; it += 2) {
-            if (it + 1 < total) load(vb, it + 1);
-            store(va, it);
-            if (it + 1 < total) {
-                if (it + 2 < total) load(va, it + 2);
-                store(vb, it + 1);
-            }
+            if (lane == 0) mbar_arrive(full_bar(ps));
+            DBG_T(w2);
+            DBG_ADD(1, w2 - w1);
+            lch += kGroups;
+            while (lch >= nchunks) { lch -= nchunks; ltile += gridDim.x; }
+            ++pq;
         }
     } else if (warp == kProdWarps + 4) {
         // ================= MMA issuer =================
+        // One thread feeds the tensor core, so its instruction stream is kept minimal: descriptors are
+        // built once and advanced by adding constants to their low word (the 14-bit address field never
+        // carries: shared memory is < 256 KB), stage / phase are counters, not divisions.
         if (lane == 0) {
             constexpr uint32_t idesc_cat = make_idesc_tf32(kRows, 2 * R, 0, 0);
             constexpr uint32_t idesc_r = make_idesc_tf32(kRows, R, 0, 0);
-            const uint32_t wbase = smem_u32(wcat);
-            int it = 0;
+            constexpr uint64_t kStepA = (uint64_t)((2 * kColChunk) >> 4);     // one K-step = two 4-column chunks of A
+            constexpr uint64_t kStepB = (uint64_t)((2 * SCW) >> 4);
+            constexpr uint64_t kLoOff = (uint64_t)(kHalfBytes >> 4);
+            const uint64_t a_desc0 = make_desc(smem_u32(stages), kColChunk, 128);
+            const uint64_t b_desc0 = make_desc(smem_u32(wcat), SCW, 128);
+            int s = 0;
+            uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int a = t & 1;
                 mbar_wait(tempty_bar(a), (uint32_t)(((t >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * kAccCols);
-                for (int ch = 0; ch < nchunks; ++ch, ++it) {
-                    const int s = it % nstage;
-                    mbar_wait(full_bar(s), (uint32_t)((it / nstage) & 1));
+                uint64_t bd = b_desc0;
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    DBG_T(m0);
+                    mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(stages + (size_t)s * kStageBytes);
-                    const uint32_t a_lo = a_hi + kHalfBytes;
+                    DBG_T(m1);
+                    DBG_ADD(3, m1 - m0);
+                    const uint64_t ad = a_desc0 + (uint64_t)s * (uint64_t)(kStageBytes >> 4);
+                    const uint32_t later = ch != 0;
 #pragma unroll
                     for (int ks = 0; ks < kCols / 8; ++ks) {
-                        const uint32_t aoff = (uint32_t)(ks * 2 * kColChunk);
-                        const uint64_t db = make_desc(wbase + (uint32_t)((ch * (kCols / 4) + ks * 2) * SCW), SCW, 128);
                         // group g = ks % NG: columns [g*2R, g*2R+R) = hi*hi, [g*2R+R, (g+1)*2R) = hi*lo
-                        umma_tf32(d_tmem + (uint32_t)((ks % NG) * 2 * R), make_desc(a_hi + aoff, kColChunk, 128), db, idesc_cat,
-                                  (ch != 0) || (ks >= NG));
-                        umma_tf32(d_tmem + (uint32_t)(NG * 2 * R), make_desc(a_lo + aoff, kColChunk, 128), db, idesc_r,
-                                  (ch | ks) != 0);
+                        umma_tf32(d_tmem + (uint32_t)((ks % NG) * 2 * R), ad + ks * kStepA, bd + ks * kStepB, idesc_cat,
+                                  ks >= NG ? 1u : later);
+                        umma_tf32(d_tmem + (uint32_t)(NG * 2 * R), ad + kLoOff + ks * kStepA, bd + ks * kStepB, idesc_r,
+                                  ks > 0 ? 1u : later);
                     }
+                    bd += (kCols / 8) * kStepB;
                     umma_commit(empty_bar(s));                       // stage reusable once these MMAs retire
                     if (ch == nchunks - 1) umma_commit(tfull_bar(a)); // accumulators complete
+                    if (++s == nstage) { s = 0; ph ^= 1u; }
+                    DBG_T(m2);
+                    DBG_ADD(4, m2 - m1);
                 }
             }
         }
     } else {
-        // ================= epilogue (warps 8-11 <-> TMEM lanes 32*(warp%4) ..) =================
+        // ================= epilogue (warps 16-19 <-> TMEM lanes 32*(warp%4) ..) =================
         const int q = warp & 3;
         const float s = scalar ? __ldg(scalar) : 1.f;
         for (int t = 0; t < my_tiles; ++t) {
             const int a = t & 1;
             const int tile = blockIdx.x + t * gridDim.x;
+            DBG_T(e0);
             mbar_wait(tfull_bar(a), (uint32_t)((t >> 1) & 1));
             tc_fence_after();
+            DBG_T(e1);
+            DBG_ADD(6, e1 - e0);
             const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kAccCols);
             float v[R];
 #pragma unroll
@@ -202,6 +241,14 @@ k_project_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
             }
         }
     }
+#ifdef GCA_TC_DEBUG
+    if (lane == 0) {
+        const long long tot = clock64() - dbg_t0;
+        if (warp == 0) { atomicAdd(&g_dbg[0], dbg_acc[0]); atomicAdd(&g_dbg[1], dbg_acc[1]); atomicAdd(&g_dbg[2], dbg_acc[2]); }
+        if (warp == kProdWarps + 4) { atomicAdd(&g_dbg[3], dbg_acc[3]); atomicAdd(&g_dbg[4], dbg_acc[4]); atomicAdd(&g_dbg[8], tot); }
+        if (warp == kProdWarps) { atomicAdd(&g_dbg[6], dbg_acc[6]); atomicAdd(&g_dbg[7], tot); }
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == kProdWarps + 4) {
@@ -231,6 +278,15 @@ int launch_project_tc_impl(const float* A, int64_t lda, const float* W, const fl
 }
 
 }  // namespace tc
+
+#ifdef GCA_TC_DEBUG
+extern "C" int gca_debug_counters(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, tc::g_dbg, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // Returns GCA_ERR_UNSUPPORTED when the shape is not on the tensor-core path (caller falls back to K1).
 int launch_project_tc(int r, bool w_is_rd, const float* A, int64_t lda, const float* W, const float* rowscale,
