@@ -12,7 +12,8 @@ import threading
 
 log = logging.getLogger("gconv_adapter_b200")
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgca.so")
+# GCA_LIB_PATH selects an alternative build of the same library (profiling experiments only).
+LIB_PATH = os.environ.get("GCA_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgca.so")
 
 GCA_OK = 0
 GCA_ERR_INDEX_RANGE = -4

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = ["gca_lib.cu", "gca_graph.cu", "gca_kernels.cu", "gca_tc_project.cu"]
-OUT = os.path.join(HERE, "lib", "libgca.so")
+OUT = os.environ.get("GCA_BUILD_OUT") or os.path.join(HERE, "lib", "libgca.so")
 
 
 def nvcc_path() -> str:

@@ -466,23 +466,15 @@ k_wgrad(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, c
 }
 
 // ------------------------------------------------------------------------------------------
-// K6: second-stage reduction of the per-CTA partials, fixed order.  A warp owns 4 column quads
-// (16 consecutive outputs); its 8 lanes per quad each sum every 8th partial, then a 3-step
-// butterfly adds the 8 lane sums.  The last CTA to finish adds up the gscalar pieces.
+// K6: second-stage reduction of the per-CTA partials, fixed order.  One warp per column quad: lane l
+// sums partials l, l+32, ... (independent loads, one round trip), a 5-step butterfly adds the 32 lane
+// sums.  The last CTA to finish adds up the gscalar pieces.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 sum_partials(const float* __restrict__ part, int np, size_t pitch, int idx4, int pl) {
+__device__ __forceinline__ float4 sum_partials(const float* __restrict__ part, int np, size_t pitch, int idx4, int lane) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int p = pl;
-    for (; p + 24 < np; p += 32) {
-        const float4 v0 = ldg4(part + (size_t)p * pitch + idx4 * 4);
-        const float4 v1 = ldg4(part + (size_t)(p + 8) * pitch + idx4 * 4);
-        const float4 v2 = ldg4(part + (size_t)(p + 16) * pitch + idx4 * 4);
-        const float4 v3 = ldg4(part + (size_t)(p + 24) * pitch + idx4 * 4);
-        acc = f4_add(acc, v0); acc = f4_add(acc, v1); acc = f4_add(acc, v2); acc = f4_add(acc, v3);
-    }
-    for (; p < np; p += 8) acc = f4_add(acc, ldg4(part + (size_t)p * pitch + idx4 * 4));
+    for (int p = lane; p < np; p += 32) acc = f4_add(acc, ldg4(part + (size_t)p * pitch + idx4 * 4));
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
+    for (int off = 1; off < 32; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
     return acc;
 }
 
@@ -495,18 +487,13 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
     const float s = scalar ? __ldg(scalar) : 1.f;
     const int rd4 = (r * d) >> 2, d4 = d >> 2, r4 = r >> 2;
     const int lane = threadIdx.x & 31;
-    const int pl = lane & 7;                       // partial lane
-    const int wq = lane >> 3;                      // which of the warp's 4 quads
     const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wtotal = gridDim.x * (blockDim.x >> 5);
     float gs = 0.f;
-    for (int base = wglobal * 4; base < rd4; base += wtotal * 4) {       // warp-uniform trip count
-        const int idx4 = base + wq;
-        const bool ok = idx4 < rd4;
-        const int q = ok ? idx4 : rd4 - 1;
-        const float4 gu = sum_partials(partGu, pu, (size_t)r * d, q, pl);
+    for (int q = wglobal; q < rd4; q += wtotal) {                        // warp-uniform
+        const float4 gu = sum_partials(partGu, pu, (size_t)r * d, q, lane);
         float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gWd) gd = sum_partials(partGd, pd, (size_t)r * d, q, pl);
-        if (ok && pl == 0) {
+        if (gWd) gd = sum_partials(partGd, pd, (size_t)r * d, q, lane);
+        if (lane == 0) {
             const int c = (q * 4) / d, k = q * 4 - c * d;
             const float g4[4] = {gu.x, gu.y, gu.z, gu.w};
 #pragma unroll
@@ -517,24 +504,18 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
             if (gWd) *reinterpret_cast<float4*>(gWd + (size_t)q * 4) = gd;
         }
     }
-    for (int base = wglobal * 4; base < d4; base += wtotal * 4) {
-        const int idx4 = base + wq;
-        const bool ok = idx4 < d4;
-        const int q = ok ? idx4 : d4 - 1;
-        const float4 cs = sum_partials(partCol, pu, (size_t)d, q, pl);
-        if (ok && pl == 0) {
+    for (int q = wglobal; q < d4; q += wtotal) {
+        const float4 cs = sum_partials(partCol, pu, (size_t)d, q, lane);
+        if (lane == 0) {
             if (gbu) *reinterpret_cast<float4*>(gbu + q * 4) = f4_scale(cs, s);
             const float4 b = ldg4(bu + q * 4);
             gs = fmaf(cs.x, b.x, fmaf(cs.y, b.y, fmaf(cs.z, b.z, fmaf(cs.w, b.w, gs))));
         }
     }
     if (gbd) {
-        for (int base = wglobal * 4; base < r4; base += wtotal * 4) {
-            const int idx4 = base + wq;
-            const bool ok = idx4 < r4;
-            const int q = ok ? idx4 : r4 - 1;
-            const float4 t = sum_partials(partBd, pb, (size_t)r, q, pl);
-            if (ok && pl == 0) *reinterpret_cast<float4*>(gbd + q * 4) = t;
+        for (int q = wglobal; q < r4; q += wtotal) {
+            const float4 t = sum_partials(partBd, pb, (size_t)r, q, lane);
+            if (lane == 0) *reinterpret_cast<float4*>(gbd + q * 4) = t;
         }
     }
     if (!gscalar) return;
@@ -795,7 +776,7 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
                                 gca_stream_t stream) {
     if (!scratch || !Wu || !bu || d <= 0 || r <= 0) return GCA_ERR_INVALID_ARG;
     const Scratch S = scratch_ptrs(const_cast<void*>(scratch), d, r);
-    int grid = ((r * d) / 16 + 7) / 8;               // one warp per 16 outputs, 8 warps per CTA
+    int grid = ((r * d) / 4 + 7) / 8;                // one warp per column quad, 8 warps per CTA
     if (grid < 1) grid = 1;
     if (grid > kMaxFin) grid = kMaxFin;
     {

@@ -138,8 +138,12 @@ k_project_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
                 const uint32_t off = (uint32_t)((jc * 8 + k4i) * kColChunk + (rl >> 3) * 128 + (rl & 7) * 16);
                 float4 hi, lo;
                 split_tf32(v[j], hi, lo);
+#ifndef GCA_TC_SKIP_STS
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + kHalfBytes + off) = lo;
+#else
+                if (hi.x == 123.456f && lo.y == 3.f) *reinterpret_cast<float4*>(st + off) = hi;
+#endif
             }
             fence_proxy_async();
             __syncwarp();
@@ -180,7 +184,13 @@ k_project_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__
                     const uint64_t ad = a_desc0 + (uint64_t)s * (uint64_t)(kStageBytes >> 4);
                     const uint32_t later = ch != 0;
 #pragma unroll
-                    for (int ks = 0; ks < kCols / 8; ++ks) {
+                    for (int ks = 0; ks < (
+#ifdef GCA_TC_SKIP_MMA
+                        1
+#else
+                        kCols / 8
+#endif
+                        ); ++ks) {
                         // group g = ks % NG: columns [g*2R, g*2R+R) = hi*hi, [g*2R+R, (g+1)*2R) = hi*lo
                         umma_tf32(d_tmem + (uint32_t)((ks % NG) * 2 * R), ad + ks * kStepA, bd + ks * kStepB, idesc_cat,
                                   ks >= NG ? 1u : later);

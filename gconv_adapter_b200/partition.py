@@ -1,0 +1,251 @@
+"""Row-partitioned GConv-Adapter over several GPUs (one process per GPU, torch.distributed / NCCL).
+
+The reference is single-process (no torch.distributed anywhere); this is the
+scale-out the north star asks for: node rows are split into contiguous blocks, every rank owns the
+rows of X / Y / all gradients and the CSR rows (targets) of its block, and only the r-wide operand of
+each sparse hop crosses NVLink:
+
+    forward : P' -> all-gather -> Z' -> all-gather -> Y            (2 gathers of [N, r] fp32)
+    backward: gH2' -> all-gather -> gH1' -> all-gather -> gX, then one all-reduce of the
+              2 d r + d + r + 1 parameter-gradient floats.
+
+Communication therefore scales with the adapter rank r, never with the hidden width d.
+
+Shards have equal size S = ceil(N / world) (the last ranks may own fewer or zero real rows), so the
+gathered buffer is [world * S, r] and a global node id is directly its row in that buffer.
+
+The dense / sparse phases themselves are the C-ABI calls of include/gca.h (``CudaPhases``); the class
+takes the phase backend as an argument only so that the orchestration (bounds, buffers, collectives)
+can be exercised on CPU with gloo by the tests, which inject their own checker backend.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _cabi
+from .finetune.gconv_adapter import GConvAdapter
+from .graphs.csr import GraphStructure
+
+
+def shard_size(num_nodes: int, world: int) -> int:
+    return (num_nodes + world - 1) // world
+
+
+def row_block(num_nodes: int, world: int, rank: int) -> tuple[int, int]:
+    """[lo, hi) of the rows owned by ``rank``; empty for trailing ranks when N < world * S."""
+    s = shard_size(num_nodes, world)
+    lo = min(num_nodes, rank * s)
+    return lo, min(num_nodes, lo + s)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class CudaPhases:
+    """Phase backend = libgca (the product path)."""
+
+    def __init__(self):
+        self.lib = _cabi.load()
+
+    @staticmethod
+    def _stream(t: torch.Tensor) -> int:
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    def build_graph(self, edge_index, num_nodes, normalize, lo, hi):
+        return GraphStructure(edge_index, num_nodes, normalize, lo, hi)
+
+    def fwd_project(self, g, x, wd, out_local):
+        d, r = x.shape[1], wd.shape[0]
+        _cabi.check(self.lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out_local.data_ptr(),
+                                             d, r, self._stream(x)), "gca_fwd_project")
+
+    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local):
+        _cabi.check(self.lib.gca_fwd_hop1(g.handle, p_full.data_ptr(), bd.data_ptr(), act, z_local.data_ptr(),
+                                          _ptr(h1_local), bd.shape[0], self._stream(p_full)), "gca_fwd_hop1")
+
+    def fwd_hop2_up(self, g, z_full, x, wu, bu, scalar, skip, h2_local, y):
+        d, r = wu.shape
+        _cabi.check(self.lib.gca_fwd_hop2_up(g.handle, z_full.data_ptr(), x.data_ptr(), x.stride(0), wu.data_ptr(),
+                                             bu.data_ptr(), _ptr(scalar), int(skip), h2_local.data_ptr(), y.data_ptr(),
+                                             y.stride(0), d, r, self._stream(x)), "gca_fwd_hop2_up")
+
+    def bwd_scratch(self, d, r, device):
+        return torch.empty(self.lib.gca_bwd_scratch_bytes(d, r), dtype=torch.uint8, device=device)
+
+    def bwd_up(self, g, gy, h2_local, wu, scalar, gh2_local, scratch):
+        d, r = wu.shape
+        _cabi.check(self.lib.gca_bwd_up(g.handle, gy.data_ptr(), gy.stride(0), h2_local.data_ptr(), wu.data_ptr(),
+                                        _ptr(scalar), gh2_local.data_ptr(), scratch.data_ptr(), d, r,
+                                        self._stream(gy)), "gca_bwd_up")
+
+    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch):
+        r = gh2_full.shape[1]
+        _cabi.check(self.lib.gca_bwd_hop2(g.handle, gh2_full.data_ptr(), z_local.data_ptr(), _ptr(h1_local), act,
+                                          gh1_local.data_ptr(), scratch.data_ptr(), r, self._stream(gh2_full)),
+                    "gca_bwd_hop2")
+
+    def bwd_hop1_down(self, g, gh1_full, x, gy, wd, scalar, skip, gp_local, gx, scratch):
+        r, d = wd.shape
+        _cabi.check(self.lib.gca_bwd_hop1_down(g.handle, gh1_full.data_ptr(), x.data_ptr(), x.stride(0), gy.data_ptr(),
+                                               gy.stride(0), wd.data_ptr(), _ptr(scalar), int(skip), gp_local.data_ptr(),
+                                               _ptr(gx), gx.stride(0) if gx is not None else d, scratch.data_ptr(),
+                                               d, r, self._stream(x)), "gca_bwd_hop1_down")
+
+    def bwd_finalize(self, scratch, wu, bu, scalar, skip, g_wd, g_bd, g_wu, g_bu, g_s):
+        d, r = wu.shape
+        _cabi.check(self.lib.gca_bwd_finalize(scratch.data_ptr(), wu.data_ptr(), bu.data_ptr(), _ptr(scalar), int(skip),
+                                              g_wd.data_ptr(), g_bd.data_ptr(), g_wu.data_ptr(), g_bu.data_ptr(),
+                                              _ptr(g_s), d, r, self._stream(wu)), "gca_bwd_finalize")
+
+
+def _all_gather_rows(full: torch.Tensor, lo: int, s: int, group) -> None:
+    """In-place all-gather: every rank contributes rows [rank*S, (rank+1)*S) of ``full``."""
+    if dist.get_world_size(group) == 1:
+        return
+    dist.all_gather_into_tensor(full, full[lo:lo + s], group=group)
+
+
+class _PartitionedFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_down, b_down, w_up, b_up, scalar, graph, act, skip, num_nodes, group, backend):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        s = shard_size(num_nodes, world)
+        lo = rank * s
+        n, d = x.shape
+        r = w_down.shape[0]
+        dev = x.device
+        w_down, b_down, w_up, b_up = (t.contiguous() for t in (w_down, b_down, w_up, b_up))
+        # padded rows (beyond N) of the gathered buffers are never referenced by any neighbour id
+        p_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
+        z_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
+        h2 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
+        h1 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev) if act == _cabi.ACT["silu"] else None
+        y = torch.empty((n, d), dtype=torch.float32, device=dev)
+        if n > 0:
+            backend.fwd_project(graph, x, w_down, p_full[lo:lo + n])
+        _all_gather_rows(p_full, lo, s, group)
+        if n > 0:
+            backend.fwd_hop1(graph, p_full, b_down, act, z_full[lo:lo + n], h1)
+        _all_gather_rows(z_full, lo, s, group)
+        if n > 0:
+            backend.fwd_hop2_up(graph, z_full, x, w_up, b_up, scalar, skip, h2, y)
+        ctx.graph, ctx.act, ctx.skip, ctx.group, ctx.backend = graph, act, skip, group, backend
+        ctx.meta = (world, s, lo, n, d, r)
+        ctx.has_scalar, ctx.has_h1 = scalar is not None, h1 is not None
+        saved = [x, w_down, w_up, b_up, z_full, h2]
+        if scalar is not None:
+            saved.append(scalar)
+        if h1 is not None:
+            saved.append(h1)
+        ctx.save_for_backward(*saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        saved = list(ctx.saved_tensors)
+        x, w_down, w_up, b_up, z_full, h2 = saved[:6]
+        rest = saved[6:]
+        scalar = rest.pop(0) if ctx.has_scalar else None
+        h1 = rest.pop(0) if ctx.has_h1 else None
+        world, s, lo, n, d, r = ctx.meta
+        backend, graph, group = ctx.backend, ctx.graph, ctx.group
+        dev = x.device
+        g_y = g_y.contiguous()
+        gh2_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
+        gh1_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
+        gp = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
+        need_x = ctx.needs_input_grad[0]
+        g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
+        # parameter gradients of this rank's rows, packed for ONE all-reduce
+        flat = torch.zeros(2 * d * r + d + r + 1, dtype=torch.float32, device=dev)
+        g_wd = flat[0:d * r].view(r, d)
+        g_wu = flat[d * r:2 * d * r].view(d, r)
+        g_bu = flat[2 * d * r:2 * d * r + d]
+        g_bd = flat[2 * d * r + d:2 * d * r + d + r]
+        g_s = flat[2 * d * r + d + r:]
+        if n > 0:
+            scratch = backend.bwd_scratch(d, r, dev)
+            backend.bwd_up(graph, g_y, h2, w_up, scalar, gh2_full[lo:lo + n], scratch)
+        _all_gather_rows(gh2_full, lo, s, group)
+        if n > 0:
+            backend.bwd_hop2(graph, gh2_full, z_full[lo:lo + n], h1, ctx.act, gh1_full[lo:lo + n], scratch)
+        _all_gather_rows(gh1_full, lo, s, group)
+        if n > 0:
+            backend.bwd_hop1_down(graph, gh1_full, x, g_y, w_down, scalar, ctx.skip, gp, g_x, scratch)
+            backend.bwd_finalize(scratch, w_up, b_up, scalar, ctx.skip, g_wd, g_bd, g_wu, g_bu,
+                                 g_s if scalar is not None else None)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return (g_x, g_wd, g_bd, g_wu, g_bu, g_s.clone() if scalar is not None else None,
+                None, None, None, None, None, None)
+
+
+class _AllReduceGrad(torch.autograd.Function):
+    """Identity whose backward sums the gradient over the ranks (for parameters used by row-local
+    torch ops after the fused kernel: LayerNorm affine, unfused scalar)."""
+
+    @staticmethod
+    def forward(ctx, t, group):
+        ctx.group = group
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        if dist.get_world_size(ctx.group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+class PartitionedGConvAdapter(GConvAdapter):
+    """``GConvAdapter`` whose forward takes this rank's ROW BLOCK of x (``row_block(N, world, rank)``)
+    and the FULL ``edge_index``; returns the same rows of the output.  Parameter gradients come back
+    already summed over ranks, so every replica applies the same optimizer step.  Only the fused
+    configuration (normalization='none') is partitioned; LayerNorm is row-local and works unchanged,
+    BatchNorm would need cross-rank statistics and is refused."""
+
+    def __init__(self, *args, process_group=None, phase_backend=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        if isinstance(self.normalization, nn.BatchNorm1d):
+            raise ValueError("PartitionedGConvAdapter: batch_norm needs global batch statistics; use 'none' or 'layer_norm'")
+        self.process_group = process_group
+        self._backend = phase_backend
+        self._graphs: dict = {}
+
+    def _graph(self, edge_index: torch.Tensor, num_nodes: int, lo: int, hi: int):
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), num_nodes, lo, hi, self.normalize)
+        hit = self._graphs.get(key)
+        if hit is None:
+            hit = (self._backend.build_graph(edge_index, num_nodes, self.normalize, lo, hi), edge_index)
+            self._graphs.clear()
+            self._graphs[key] = hit
+        return hit[0]
+
+    def forward(self, x_local: torch.Tensor, edge_index: torch.Tensor, num_nodes: int, edge_attr=None) -> torch.Tensor:
+        if self._backend is None:
+            self._backend = CudaPhases()
+        group = self.process_group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        lo, hi = row_block(num_nodes, world, rank)
+        if x_local.shape != (hi - lo, self.hidden_size):
+            raise RuntimeError(f"rank {rank} owns rows [{lo}, {hi}); expected x_local of shape {(hi - lo, self.hidden_size)}")
+        if self.hidden_size % 4 != 0 or self.bottleneck_size not in (8, 16, 32, 64):
+            raise RuntimeError("PartitionedGConvAdapter needs hidden % 4 == 0 and bottleneck in {8,16,32,64}")
+        graph = self._graph(edge_index, num_nodes, lo, hi)
+        x_local = x_local.contiguous()
+        fused_scalar = self.scalar if self.normalization is None else None
+        out = _PartitionedFunction.apply(x_local, self.conv_down.lin.weight, self.conv_down.bias,
+                                         self.conv_up.lin.weight, self.conv_up.bias, fused_scalar, graph, self._act,
+                                         self.skip_connection, num_nodes, group, self._backend)
+        if isinstance(self.normalization, nn.LayerNorm):
+            ln = self.normalization
+            out = torch.nn.functional.layer_norm(out, ln.normalized_shape, _AllReduceGrad.apply(ln.weight, group),
+                                                 _AllReduceGrad.apply(ln.bias, group), ln.eps)
+            if self.scalar is not None:
+                out = out * _AllReduceGrad.apply(self.scalar, group)
+        return out

@@ -1,0 +1,118 @@
+"""Multi-GPU leg of bench.py: the workload graph row-partitioned over the ranks of one node
+(torchrun: one process per GPU, NCCL), fwd + bwd per step, device-timed, max over ranks."""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def run_partitioned(args, metric: str, unit: str) -> None:
+    from . import _cabi
+    from .graphs.synthetic import SHAPES, make_graph, make_inputs
+    from .partition import PartitionedGConvAdapter, row_block
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+    name = args.workload or "arxiv"
+    ei, n = make_graph(name, seed=0, power_law=args.power_law)       # every rank builds the same graph
+    shp = SHAPES[name]
+    d, r = shp.hidden, shp.rank
+    e = ei.size(1)
+    lo, hi = row_block(n, world, rank)
+    # only this rank's rows of X / gY are materialised on the device
+    gen = torch.Generator().manual_seed(1000 + rank)
+    x_local = torch.randn(hi - lo, d, generator=gen)
+    g_local = torch.randn(hi - lo, d, generator=gen)
+    _, _, params = make_inputs(8, d, r, seed=0)
+    m = PartitionedGConvAdapter(d, r, learnable_scalar=True)
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k, v in params.items():
+            sd[k].copy_(v)
+    m = m.to(dev)
+    eid = ei.to(dev)
+    xd = x_local.to(dev).requires_grad_(True)
+    gd = g_local.to(dev)
+
+    def step():
+        xd.grad = None
+        for p in m.parameters():
+            p.grad = None
+        y = m(xd, eid, n)
+        y.backward(gd)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.gca_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([lib.gca_launch_count() - l0], device=dev)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+
+    # e2e: host rows -> device, fwd + bwd, loss back to the host, every step
+    x_host = x_local.pin_memory()
+    x_dev = torch.empty_like(xd)
+
+    def e2e_step():
+        for p in m.parameters():
+            p.grad = None
+        x_dev.copy_(x_host, non_blocking=True)
+        xin = x_dev.detach().requires_grad_(True)
+        y = m(xin, eid, n)
+        loss = (y * gd).sum()
+        loss.backward()
+        return loss.item()
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    k2 = max(5, args.steps // 3)
+    t0.record()
+    for _ in range(k2):
+        e2e_step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([t0.elapsed_time(t1) / k2], device=dev)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        ms_step = ms.item()
+        nr = 4 * n * r
+        line = {
+            "metric": metric, "value": e / (ms_step / 1e3), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}-shaped: N={n} E={e} hidden={d} rank={r}",
+                       "parallelism": f"row partition over {world} GPUs, 4 all-gathers of [N, r] fp32 "
+                                      f"({nr / 1e6:.1f} MB each) + 1 all-reduce of {2 * d * r + d + r + 1} floats per step",
+                       "l2": "per-rank X/gY/Y/gX are %d MB each" % (4 * (hi - lo) * d // 1_000_000)},
+            "e2e": {"value": e / (ms2.item() / 1e3), "unit": unit, "h2d_bytes_per_step": 4 * n * d,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": round(ms2.item(), 4), "steps": k2},
+            "gpu_launches": int(launches.item()),
+            "roofline": None, "cpu_baseline": None,
+            "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on the N=1 run only"]},
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
