@@ -11,6 +11,8 @@
 // Reference semantics: /root/reference/src/finetune/gconv_adapter.py:92-106 (see include/gca.h).
 // Sparse rows are processed by lane groups (R/4 lanes x 128-bit loads per neighbour row); rows
 // longer than kLongRow are swept by the whole warp.  All reductions have a fixed order.
+#include <cstdlib>
+
 #include "gca_common.cuh"
 
 namespace gca {
@@ -466,13 +468,409 @@ k_wgrad(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, c
 }
 
 // ------------------------------------------------------------------------------------------
+// Register-level tensor-core helpers (mma.sync m16n8k8, tf32 inputs, fp32 accumulate; 279 TFLOP/s
+// measured on B200, 4x the fp32 FMA pipe).  fp32 parity needs the 3xTF32 split: x = hi + lo and
+//   A B ~= A_hi B_hi + A_lo B_hi + A_hi B_lo.
+// Fragment layout (g = lane >> 2, t = lane & 3):
+//   A 16x8: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)      B 8x8: b0 (k=t, n=g)  b1 (k=t+4, n=g)
+//   C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+// A 32-column block is handled as 4 n-tiles with the column permutation  col = cb + 4 n + j  (j = n-tile),
+// so that lane (g, t) loads ONE float4 (cols cb+4g .. +3) per row for all four tiles - a warp instruction
+// reads 4 rows x 128 contiguous bytes - and owns 8 consecutive output columns cb+8t .. cb+8t+7.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// hi = x with the 13 low mantissa bits cleared (exact tf32), lo = tf32_rn(x - hi)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1-mma: out[i, 0:R] = rowscale[i] * s * sum_k A[i,k] W[k, 0:R] with M = rows, N = R, K = columns of A.
+// A-fragments come straight from global memory: lane (g, t) loads the float4 A[row g (+8)][kb + 4t .. +3] of a
+// 16-column block kb (8 rows x 64 contiguous bytes per warp instruction) and uses it for two k-steps through
+// the K permutation  k-step s: logical k = t -> column kb+4t+2s, logical k = t+4 -> column kb+4t+2s+1.
+// W sits in shared memory as {b0_hi, b1_hi, b0_lo, b1_lo} quads in exactly that order, one LDS.128 per
+// (k-step, n-tile).  Products go to 2 accumulator sets (alternating 16-column blocks) + 1 for the lo terms.
+// ------------------------------------------------------------------------------------------
+template <int R, bool W_IS_RD>
+__global__ void __launch_bounds__(256, 2)
+k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ rowscale,
+              const float* __restrict__ scalar, float* __restrict__ out, int n, int d) {
+    constexpr int NT = R / 8;                       // n-tiles
+    extern __shared__ __align__(16) uint32_t smem_u[];
+    // Wq[kb][s][nt][g][t] = uint4 {hi(k0,c), hi(k1,c), lo(k0,c), lo(k1,c)}, k0 = kb*16+4t+2s, k1 = k0+1, c = nt*8+g
+    // (lane = 4g + t reads consecutive 16-byte slots: conflict-free LDS.128)
+    uint4* Wq = reinterpret_cast<uint4*>(smem_u);
+    const int nkb = d >> 4;                         // 16-column blocks (d % 16 == 0)
+    for (int idx = threadIdx.x; idx < nkb * 2 * 4 * NT * 8; idx += blockDim.x) {
+        int r_ = idx;
+        const int t_ = r_ & 3; r_ >>= 2;
+        const int g_ = r_ & 7; r_ >>= 3;
+        const int nt_ = r_ % NT; r_ /= NT;
+        const int s_ = r_ & 1; const int kb_ = r_ >> 1;
+        const int k0 = kb_ * 16 + 4 * t_ + 2 * s_, c = nt_ * 8 + g_;
+        const float w0 = W_IS_RD ? W[(size_t)c * d + k0] : W[(size_t)k0 * R + c];
+        const float w1 = W_IS_RD ? W[(size_t)c * d + k0 + 1] : W[(size_t)(k0 + 1) * R + c];
+        uint4 q;
+        split_tf32(w0, q.x, q.z);
+        split_tf32(w1, q.y, q.w);
+        Wq[idx] = q;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const float sc_s = scalar ? __ldg(scalar) : 1.f;
+    const int nmt = (n + 15) / 16;                  // 16-row m-tiles
+    const int wglobal = blockIdx.x * 8 + warp, wtotal = gridDim.x * 8;
+    for (int mt = wglobal; mt < nmt; mt += wtotal) {
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const float* p0 = A + (size_t)min(r0, n - 1) * lda + 4 * t;
+        const float* p1 = A + (size_t)min(r1, n - 1) * lda + 4 * t;
+        float acc[3][NT][4];
+#pragma unroll
+        for (int a_ = 0; a_ < 3; ++a_)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[a_][j][i] = 0.f;
+        for (int kb0 = 0; kb0 < nkb; kb0 += 4) {    // 4 blocks = 8 loads in flight per lane
+            float4 x0[4], x1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kb0 + u < nkb) {
+                    x0[u] = ldg4_stream(p0 + (kb0 + u) * 16);
+                    x1[u] = ldg4_stream(p1 + (kb0 + u) * 16);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kb0 + u >= nkb) break;
+                const float e0[4] = {x0[u].x, x0[u].y, x0[u].z, x0[u].w};
+                const float e1[4] = {x1[u].x, x1[u].y, x1[u].z, x1[u].w};
+#pragma unroll
+                for (int s_ = 0; s_ < 2; ++s_) {
+                    uint32_t ah[4], al[4];
+                    split_tf32(e0[2 * s_], ah[0], al[0]);        // (row g,   k = t)
+                    split_tf32(e1[2 * s_], ah[1], al[1]);        // (row g+8, k = t)
+                    split_tf32(e0[2 * s_ + 1], ah[2], al[2]);    // (row g,   k = t+4)
+                    split_tf32(e1[2 * s_ + 1], ah[3], al[3]);    // (row g+8, k = t+4)
+                    const uint4* wq = Wq + (((kb0 + u) * 2 + s_) * NT) * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const uint4 q = wq[j * 32];
+                        mma_tf32(acc[u & 1][j], ah, q.x, q.y);
+                        mma_tf32(acc[2][j], al, q.x, q.y);
+                        mma_tf32(acc[2][j], ah, q.z, q.w);
+                    }
+                }
+            }
+        }
+        const float sc0 = (r0 < n ? (rowscale ? __ldg(rowscale + r0) : 1.f) : 0.f) * sc_s;
+        const float sc1 = (r1 < n ? (rowscale ? __ldg(rowscale + r1) : 1.f) : 0.f) * sc_s;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (acc[0][j][i] + acc[1][j][i]) + acc[2][j][i];
+            if (r0 < n) *reinterpret_cast<float2*>(out + (size_t)r0 * R + j * 8 + 2 * t) = make_float2(v[0] * sc0, v[1] * sc0);
+            if (r1 < n) *reinterpret_cast<float2*>(out + (size_t)r1 * R + j * 8 + 2 * t) = make_float2(v[2] * sc1, v[3] * sc1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3-mma: same contract as k_hop_expand, with the [64, R] x [R, d] expansion on the tensor core:
+// M = rows (4 m-tiles of 16 per tile), N = output columns, K = R.  The gathered H tile is split into tf32
+// hi / lo when it is staged in shared memory; W^T sits in shared memory with an odd row stride so the
+// B-fragment loads are conflict-free.  Warp w owns the 32-column blocks w, w+8, ...: lane (g, t) reads the
+// residual and writes the output as two float4 (columns cb+8t .. +7) for rows g and g+8 of every m-tile, i.e.
+// 8 rows x 128 contiguous bytes per warp instruction.
+// ------------------------------------------------------------------------------------------
+template <int R, bool W_IS_DR>
+__global__ void __launch_bounds__(256, 2)
+k_hop_expand_mma(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
+                 const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
+                 const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
+                 int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
+                 int n, int d) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    constexpr int RS = R + 4;                       // padded row stride of the H tile
+    constexpr int KS = R / 8;                       // k-steps
+    extern __shared__ __align__(16) uint32_t smem_u[];
+    const int WS = d + 1;                           // odd row stride of W^T
+    uint32_t* Wh = smem_u;                          // [R][WS]  tf32 hi
+    uint32_t* Wl = Wh + (size_t)R * WS;             // [R][WS]  tf32 lo
+    uint32_t* Hh = Wl + (size_t)R * WS;             // [64][RS]
+    uint32_t* Hl = Hh + kTileRows * RS;
+    if (Out) {
+        for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
+            int k, c;
+            if (W_IS_DR) { k = idx / R; c = idx - k * R; } else { c = idx / d; k = idx - c * d; }
+            uint32_t hi, lo;
+            split_tf32(W[idx], hi, lo);
+            Wh[c * WS + k] = hi;
+            Wl[c * WS + k] = lo;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPG, grp = lane / LPG;
+    const int g = lane >> 2, t = lane & 3;
+    const float s = scalar ? __ldg(scalar) : 1.f;
+    const float alpha = alpha_is_scalar ? s : 1.f;
+    const float beta = use_resid ? s : 0.f;
+    const int nblk = (d + 31) / 32;
+    const int ntiles = (n + kTileRows - 1) / kTileRows;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int trow = tile * kTileRows;
+        __syncthreads();              // W ready / previous tile's readers of the H tile are done
+        for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
+            const int row = trow + rr + grp;
+            const bool valid = row < n;
+            const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                h = f4_scale(acc, __ldg(dis + row));
+                *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
+            }
+            uint4 hi, lo;
+            split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(&Hh[(rr + grp) * RS + sub * 4]) = hi;
+            *reinterpret_cast<uint4*>(&Hl[(rr + grp) * RS + sub * 4]) = lo;
+        }
+        __syncthreads();
+        if (!Out) continue;
+        for (int blk = warp; blk < nblk; blk += 8) {
+            const int cb = blk * 32;
+            // column permutation inside the 32-column block: n-tile j, n -> col = cb + 4 * perm(n) + j with
+            // perm(2t) = t, perm(2t+1) = 4 + t, so the C-fragments of lane (g, t) are the float4s at cb + 4t and
+            // cb + 16 + 4t: every load / store instruction covers 64 contiguous bytes (two full sectors) per row.
+            const int lc = cb + 4 * ((g >> 1) + 4 * (g & 1));   // B-fragment columns of this lane: lc + j
+            const bool lc_ok = lc < d;
+            // W fragments of this block: b0 = W[c = 8 ks + t][lc + j], b1 = W[c = 8 ks + t + 4][lc + j]
+            uint32_t wh[KS][4][2], wl[KS][4][2];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int c = ks * 8 + t + 4 * h2;
+                        wh[ks][j][h2] = lc_ok ? Wh[c * WS + lc + j] : 0u;
+                        wl[ks][j][h2] = lc_ok ? Wl[c * WS + lc + j] : 0u;
+                    }
+            const int oc = cb + 4 * t, oc1 = cb + 16 + 4 * t;    // output column quads of this lane
+            const bool o0 = oc < d, o1 = oc1 < d;
+            float4 b4a = make_float4(0.f, 0.f, 0.f, 0.f), b4b = b4a;
+            if (bias) { if (o0) b4a = ldg4(bias + oc); if (o1) b4b = ldg4(bias + oc1); }
+#pragma unroll 2
+            for (int mt = 0; mt < kTileRows / 16; ++mt) {
+                const int r0 = trow + mt * 16 + g, r1 = r0 + 8;
+                float4 x0a, x0b, x1a, x1b;
+                x0a = x0b = x1a = x1b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (use_resid) {
+                    if (r0 < n) { if (o0) x0a = ldg4_stream(resid + (size_t)r0 * ldr + oc); if (o1) x0b = ldg4_stream(resid + (size_t)r0 * ldr + oc1); }
+                    if (r1 < n) { if (o0) x1a = ldg4_stream(resid + (size_t)r1 * ldr + oc); if (o1) x1b = ldg4_stream(resid + (size_t)r1 * ldr + oc1); }
+                }
+                float acc[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint32_t ah[4], al[4];
+                    const int hr = (mt * 16 + g) * RS + ks * 8 + t;
+                    ah[0] = Hh[hr]; ah[1] = Hh[hr + 8 * RS]; ah[2] = Hh[hr + 4]; ah[3] = Hh[hr + 8 * RS + 4];
+                    al[0] = Hl[hr]; al[1] = Hl[hr + 8 * RS]; al[2] = Hl[hr + 4]; al[3] = Hl[hr + 8 * RS + 4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mma_tf32(acc[j], ah, wh[ks][j][0], wh[ks][j][1]);
+                        mma_tf32(acc[j], al, wh[ks][j][0], wh[ks][j][1]);
+                        mma_tf32(acc[j], ah, wl[ks][j][0], wl[ks][j][1]);
+                    }
+                }
+                // acc[j][0] = (row g, col oc + j), [1] = (row g, col oc1 + j), [2] / [3] = row g + 8
+                auto fin = [&](float a0, float a1, float a2, float a3, const float4& b4, const float4& x) {
+                    float4 y = make_float4(alpha * (a0 + b4.x), alpha * (a1 + b4.y), alpha * (a2 + b4.z), alpha * (a3 + b4.w));
+                    if (use_resid) {
+                        y.x = fmaf(beta, x.x, y.x); y.y = fmaf(beta, x.y, y.y); y.z = fmaf(beta, x.z, y.z); y.w = fmaf(beta, x.w, y.w);
+                    }
+                    return y;
+                };
+                if (r0 < n) {
+                    if (o0) stg4_stream(Out + (size_t)r0 * ldo + oc, fin(acc[0][0], acc[1][0], acc[2][0], acc[3][0], b4a, x0a));
+                    if (o1) stg4_stream(Out + (size_t)r0 * ldo + oc1, fin(acc[0][1], acc[1][1], acc[2][1], acc[3][1], b4b, x0b));
+                }
+                if (r1 < n) {
+                    if (o0) stg4_stream(Out + (size_t)r1 * ldo + oc, fin(acc[0][2], acc[1][2], acc[2][2], acc[3][2], b4a, x1a));
+                    if (o1) stg4_stream(Out + (size_t)r1 * ldo + oc1, fin(acc[0][3], acc[1][3], acc[2][3], acc[3][3], b4b, x1b));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4-mma: G[c, k] = sum_i H[i, c] A[i, k]  (+ colsum, dot) with M = c, N = k (columns of A), K = rows.
+// CTA = 8 warps = 8 column blocks of 32; every warp sweeps ALL rows of the CTA's tiles for its block, so
+// no cross-warp reduction is needed.  Per 128-row tile the products are accumulated by the tensor core,
+// then folded into a running fp32 sum with a plain FADD (the tensor core's accumulator truncates; 48
+// updates per fold keep that bias ~1e-7).  A is read straight from global memory into B-fragments.
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaRows = 128;
+
+template <int R>
+__global__ void __launch_bounds__(256, R == 16 ? 2 : 1)
+k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, const float* __restrict__ B, int64_t ldb,
+            float* __restrict__ partG, float* __restrict__ partCol, float* __restrict__ partDot, int* header, int header_slot,
+            int n, int d, int col_base) {
+    constexpr int MT = R / 16;            // m-tiles (16 c's each)
+    constexpr int RS = R + 8;             // padded row stride of the H tile (conflict-free A-fragment loads)
+    __shared__ __align__(16) uint32_t Hh[kMmaRows * RS];
+    __shared__ __align__(16) uint32_t Hl[kMmaRows * RS];
+    __shared__ float s_dot[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int cb = col_base + warp * 32;                 // this warp's column block
+    const int col = cb + 4 * g;                          // this lane's float4 of columns
+    const bool col_ok = col < d;                         // d % 4 == 0
+    float run[MT][4][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) run[m][j][i] = 0.f;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dot = 0.f;
+    const int ntiles = (n + kMmaRows - 1) / kMmaRows;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * kMmaRows;
+        const int rows = min(kMmaRows, n - row0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kMmaRows * (R / 4); idx += blockDim.x) {
+            const int r_ = idx / (R / 4), c4 = idx - r_ * (R / 4);
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r_ < rows) h = ldg4(H + (size_t)(row0 + r_) * R + c4 * 4);
+            uint4 hi, lo;
+            split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(&Hh[r_ * RS + c4 * 4]) = hi;
+            *reinterpret_cast<uint4*>(&Hl[r_ * RS + c4 * 4]) = lo;
+        }
+        __syncthreads();
+        float acc[MT][4][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[m][j][i] = 0.f;
+        const float* a0p = A + (size_t)row0 * lda + col;
+        const float* b0p = B ? B + (size_t)row0 * ldb + col : nullptr;
+        // 4 k-steps (32 rows) per iteration: 8 loads in flight per lane
+        for (int k0 = 0; k0 < kMmaRows; k0 += 32) {
+            if (k0 >= rows) break;
+            float4 v[4][2], w[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r_ = k0 + u * 8 + t + 4 * h2;
+                    const bool ok = col_ok && r_ < rows;
+                    v[u][h2] = ok ? ldg4_stream(a0p + (size_t)r_ * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0p) w[u][h2] = ok ? ldg4_stream(b0p + (size_t)r_ * ldb) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u * 8 >= rows) break;               // warp-uniform
+                uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    split_tf32(v[u][h2].x, bh[h2][0], bl[h2][0]); split_tf32(v[u][h2].y, bh[h2][1], bl[h2][1]);
+                    split_tf32(v[u][h2].z, bh[h2][2], bl[h2][2]); split_tf32(v[u][h2].w, bh[h2][3], bl[h2][3]);
+                    csum = f4_add(csum, v[u][h2]);
+                    if (b0p) dot = fmaf(v[u][h2].x, w[u][h2].x, fmaf(v[u][h2].y, w[u][h2].y,
+                                   fmaf(v[u][h2].z, w[u][h2].z, fmaf(v[u][h2].w, w[u][h2].w, dot))));
+                }
+                const int kr = k0 + u * 8 + t;               // rows kr (k = t) and kr + 4 (k = t + 4)
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    uint32_t ah[4], al[4];
+                    ah[0] = Hh[kr * RS + m * 16 + g];       ah[1] = Hh[kr * RS + m * 16 + g + 8];
+                    ah[2] = Hh[(kr + 4) * RS + m * 16 + g]; ah[3] = Hh[(kr + 4) * RS + m * 16 + g + 8];
+                    al[0] = Hl[kr * RS + m * 16 + g];       al[1] = Hl[kr * RS + m * 16 + g + 8];
+                    al[2] = Hl[(kr + 4) * RS + m * 16 + g]; al[3] = Hl[(kr + 4) * RS + m * 16 + g + 8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mma_tf32(acc[m][j], ah, bh[0][j], bh[1][j]);
+                        mma_tf32(acc[m][j], al, bh[0][j], bh[1][j]);
+                        mma_tf32(acc[m][j], ah, bl[0][j], bl[1][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) run[m][j][i] += acc[m][j][i];
+    }
+    // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns cb+8t .. cb+8t+7 ----
+    float* pg = partG + (size_t)blockIdx.x * R * d;
+    const int oc = cb + 8 * t;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {               // c = g (+8)
+            const int c = m * 16 + g + 8 * half;
+            const int i0 = 2 * half;                          // c0/c1 for row g, c2/c3 for row g+8
+            if (oc < d)
+                *reinterpret_cast<float4*>(pg + (size_t)c * d + oc) =
+                    make_float4(run[m][0][i0], run[m][1][i0], run[m][2][i0], run[m][3][i0]);
+            if (oc + 4 < d)
+                *reinterpret_cast<float4*>(pg + (size_t)c * d + oc + 4) =
+                    make_float4(run[m][0][i0 + 1], run[m][1][i0 + 1], run[m][2][i0 + 1], run[m][3][i0 + 1]);
+        }
+    }
+    // column sums: add the 4 row-lanes (t) of every column quad
+    csum = f4_add(csum, f4_shfl_xor(csum, 1));
+    csum = f4_add(csum, f4_shfl_xor(csum, 2));
+    if (partCol && t == 0 && col_ok) *reinterpret_cast<float4*>(partCol + (size_t)blockIdx.x * d + col) = csum;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (lane == 0) s_dot[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (partDot) {
+            float tsum = 0.f;
+            for (int w_ = 0; w_ < 8; ++w_) tsum += s_dot[w_];
+            if (col_base == 0) partDot[blockIdx.x] = tsum; else partDot[blockIdx.x] += tsum;   // launches are stream-ordered
+        }
+        if (blockIdx.x == 0) header[header_slot] = gridDim.x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K6: second-stage reduction of the per-CTA partials, fixed order.  One warp per column quad: lane l
 // sums partials l, l+32, ... (independent loads, one round trip), a 5-step butterfly adds the 32 lane
 // sums.  The last CTA to finish adds up the gscalar pieces.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 sum_partials(const float* __restrict__ part, int np, size_t pitch, int idx4, int lane) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = lane; p < np; p += 32) acc = f4_add(acc, ldg4(part + (size_t)p * pitch + idx4 * 4));
+    const float* base = part + (size_t)idx4 * 4;
+    int p = lane;
+    for (; p + 96 < np; p += 128) {              // four independent loads in flight
+        const float4 v0 = ldg4(base + (size_t)p * pitch), v1 = ldg4(base + (size_t)(p + 32) * pitch);
+        const float4 v2 = ldg4(base + (size_t)(p + 64) * pitch), v3 = ldg4(base + (size_t)(p + 96) * pitch);
+        acc = f4_add(acc, f4_add(f4_add(v0, v1), f4_add(v2, v3)));
+    }
+    for (; p < np; p += 32) acc = f4_add(acc, ldg4(base + (size_t)p * pitch));
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
     return acc;
@@ -560,6 +958,27 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
                    float* out, int n, int d, cudaStream_t st) {
     if (n == 0) return GCA_OK;
     if (tc_enabled()) {
+        // two tensor-core variants: tcgen05 (UMMA + TMEM, shared-memory operand pipeline) and register-level
+        // mma.sync (operands straight from global memory).  GCA_PROJECT=tcgen05|mma picks one; default = mma,
+        // which measured faster at these skinny shapes (N = r <= 32 makes the tcgen05 path shared-memory bound).
+        static const int prefer_tcgen05 = [] { const char* e = getenv("GCA_PROJECT"); return (e && e[0] == 't') ? 1 : 0; }();
+        if constexpr (R == 16 || R == 32) {
+            if (!prefer_tcgen05 && d % 16 == 0) {
+                const size_t smem_m = sizeof(uint4) * (size_t)(d / 16) * 2 * 4 * (R / 8) * 8;
+                if (smem_m <= 100 * 1024) {
+                    GCA_TRY(set_smem(k_project_mma<R, W_IS_RD>, smem_m));
+                    const int nmt = (n + 15) / 16;
+                    int grid_m = (nmt + 7) / 8;
+                    if (grid_m > 2 * num_sms()) grid_m = 2 * num_sms();
+                    {
+                        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
+                        k_project_mma<R, W_IS_RD><<<grid_m, 256, smem_m, st>>>(A, lda, W, rowscale, scalar, out, n, d);
+                    }
+                    GCA_LAUNCH_OK();
+                    return GCA_OK;
+                }
+            }
+        }
         const int st_tc = launch_project_tc(R, W_IS_RD, A, lda, W, rowscale, scalar, out, n, d, st);
         if (st_tc != GCA_ERR_UNSUPPORTED) return st_tc;
     }
@@ -598,6 +1017,23 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
                       const float* bias, const float* resid, int64_t ldr, const float* scalar, int alpha_is_scalar,
                       int use_resid, float* Hout, float* Out, int64_t ldo, int n, int d, cudaStream_t st) {
     if (n == 0) return GCA_OK;
+    if constexpr (R == 16 || R == 32) {
+        if (tc_enabled()) {
+            const size_t smem_m = sizeof(uint32_t) * ((size_t)2 * R * (d + 1) + (size_t)2 * kTileRows * (R + 4));
+            if (smem_m <= 100 * 1024) {
+                GCA_TRY(set_smem(k_hop_expand_mma<R, W_IS_DR>, smem_m));
+                const int ntiles_m = (n + kTileRows - 1) / kTileRows;
+                const int grid_m = ntiles_m < 2 * num_sms() ? ntiles_m : 2 * num_sms();
+                {
+                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                    k_hop_expand_mma<R, W_IS_DR><<<grid_m, 256, smem_m, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
+                                                                              alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+                }
+                GCA_LAUNCH_OK();
+                return GCA_OK;
+            }
+        }
+    }
     const size_t smem = sizeof(float) * ((size_t)R * d + (size_t)kTileRows * R);
     if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
     GCA_TRY(set_smem(k_hop_expand<R, W_IS_DR>, smem));
@@ -615,6 +1051,21 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
 template <int R>
 int launch_wgrad(const float* A, int64_t lda, const float* H, const float* B, int64_t ldb, float* partG, float* partCol,
                  float* partDot, int* header, int slot, int n, int d, cudaStream_t st) {
+    if constexpr (R == 16 || R == 32) {
+        if (tc_enabled()) {
+            const int ntiles = (n + kMmaRows - 1) / kMmaRows;
+            int grid = ntiles < 1 ? 1 : ntiles;
+            const int cap = kMaxParts < 2 * num_sms() ? kMaxParts : 2 * num_sms();
+            if (grid > cap) grid = cap;
+            for (int col0 = 0; col0 < d; col0 += 256) {
+                ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st);
+                k_wgrad_mma<R><<<grid, 256, 0, st>>>(A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d, col0);
+                count_launch();
+            }
+            GCA_CUDA(cudaGetLastError());
+            return GCA_OK;
+        }
+    }
     constexpr int CW = R < 16 ? R : 16, CB = R / CW;
     constexpr int kMaxWarps = 12;
     const int max_chunks = kMaxWarps / CB;                 // column chunks (128 wide) per launch
