@@ -716,6 +716,154 @@ k_hop_expand_mma(const int* __restrict__ rowptr, const int* __restrict__ colidx,
 }
 
 // ------------------------------------------------------------------------------------------
+// K3-ws: warp-specialised, persistent variant of K3-mma (one 512-thread CTA per SM).
+//   warps 0-7  ("gather"): the latency-bound r-wide SpMM of tile k+1 -> H tile buffer (k+1) & 1 (+ Hout)
+//   warps 8-15 ("expand"): tensor-core expansion + residual + store of tile k; warp w owns the 32-column blocks
+//              w-8, w, ...; the residual rows of the NEXT tile are prefetched m-tile by m-tile into the
+//              registers the current tile has just released, so 16 float4 per lane are always in flight.
+// Hand-over with named barriers (bar.sync / bar.arrive, 512 participants each): FULL[b] gather -> expand,
+// EMPTY[b] expand -> gather.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int R, bool W_IS_DR>
+__global__ void __launch_bounds__(512, 1)
+k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
+                const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
+                const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
+                int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
+                int n, int d) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    constexpr int RS = R + 4;
+    constexpr int KS = R / 8;
+    constexpr int MTS = kTileRows / 16;             // m-tiles per tile (4)
+    constexpr int kFull = 1, kEmpty = 3;            // named barrier ids: kFull + b, kEmpty + b
+    extern __shared__ __align__(16) uint32_t smem_u[];
+    const int WS = d + 1;
+    uint32_t* Wh = smem_u;                          // [R][WS]
+    uint32_t* Wl = Wh + (size_t)R * WS;
+    uint32_t* Hbuf = Wl + (size_t)R * WS;           // [2 buffers][hi, lo][64][RS]
+    for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
+        int k, c;
+        if (W_IS_DR) { k = idx / R; c = idx - k * R; } else { c = idx / d; k = idx - c * d; }
+        uint32_t hi, lo;
+        split_tf32(W[idx], hi, lo);
+        Wh[c * WS + k] = hi;
+        Wl[c * WS + k] = lo;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntiles = (n + kTileRows - 1) / kTileRows;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < 8) {
+        // ===================== gather warps =====================
+        const int sub = lane % LPG, grp = lane / LPG;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int b = k & 1;
+            const int trow = (blockIdx.x + k * gridDim.x) * kTileRows;
+            if (k >= 2) named_sync(kEmpty + b, 512);           // expand warps are done with this buffer
+            uint32_t* Hh = Hbuf + (size_t)b * 2 * kTileRows * RS;
+            uint32_t* Hl = Hh + kTileRows * RS;
+            for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
+                const int row = trow + rr + grp;
+                const bool valid = row < n;
+                const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+                    h = f4_scale(acc, __ldg(dis + row));
+                    *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
+                }
+                uint4 hi, lo;
+                split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+                *reinterpret_cast<uint4*>(&Hh[(rr + grp) * RS + sub * 4]) = hi;
+                *reinterpret_cast<uint4*>(&Hl[(rr + grp) * RS + sub * 4]) = lo;
+            }
+            __threadfence_block();
+            named_arrive(kFull + b, 512);
+        }
+    } else {
+        // ===================== expand warps =====================
+        const int g = lane >> 2, t = lane & 3;
+        const int ew = warp - 8;
+        const float s = scalar ? __ldg(scalar) : 1.f;
+        const float alpha = alpha_is_scalar ? s : 1.f;
+        const float beta = use_resid ? s : 0.f;
+        const int nblk = (d + 31) / 32;
+        // this kernel is launched only when nblk <= 8: one column block per expand warp
+        const int cb = ew * 32;
+        const bool blk_ok = ew < nblk;
+        const int lc = cb + 4 * ((g >> 1) + 4 * (g & 1));
+        const bool lc_ok = lc < d;
+        const int oc = cb + 4 * t, oc1 = cb + 16 + 4 * t;
+        const bool o0 = blk_ok && oc < d, o1 = blk_ok && oc1 < d;
+        float4 b4a = make_float4(0.f, 0.f, 0.f, 0.f), b4b = b4a;
+        if (bias) { if (o0) b4a = ldg4(bias + oc); if (o1) b4b = ldg4(bias + oc1); }
+        float4 x[MTS][4];                                       // residual of (row g, oc) (row g, oc1) (row g+8, ..)
+        auto prefetch = [&](int k, int mt) {
+            const int r0 = (blockIdx.x + k * gridDim.x) * kTileRows + mt * 16 + g, r1 = r0 + 8;
+            x[mt][0] = x[mt][1] = x[mt][2] = x[mt][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_resid && k < my_tiles) {
+                if (r0 < n) { if (o0) x[mt][0] = ldg4_stream(resid + (size_t)r0 * ldr + oc); if (o1) x[mt][1] = ldg4_stream(resid + (size_t)r0 * ldr + oc1); }
+                if (r1 < n) { if (o0) x[mt][2] = ldg4_stream(resid + (size_t)r1 * ldr + oc); if (o1) x[mt][3] = ldg4_stream(resid + (size_t)r1 * ldr + oc1); }
+            }
+        };
+#pragma unroll
+        for (int mt = 0; mt < MTS; ++mt) prefetch(0, mt);
+        for (int k = 0; k < my_tiles; ++k) {
+            const int b = k & 1;
+            const int trow = (blockIdx.x + k * gridDim.x) * kTileRows;
+            named_sync(kFull + b, 512);
+            const uint32_t* Hh = Hbuf + (size_t)b * 2 * kTileRows * RS;
+            const uint32_t* Hl = Hh + kTileRows * RS;
+#pragma unroll
+            for (int mt = 0; mt < MTS; ++mt) {
+                float acc[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+                if (blk_ok) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        uint32_t ah[4], al[4];
+                        const int hr = (mt * 16 + g) * RS + ks * 8 + t;
+                        ah[0] = Hh[hr]; ah[1] = Hh[hr + 8 * RS]; ah[2] = Hh[hr + 4]; ah[3] = Hh[hr + 8 * RS + 4];
+                        al[0] = Hl[hr]; al[1] = Hl[hr + 8 * RS]; al[2] = Hl[hr + 4]; al[3] = Hl[hr + 8 * RS + 4];
+                        const int c0 = ks * 8 + t;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t bh0 = lc_ok ? Wh[c0 * WS + lc + j] : 0u, bh1 = lc_ok ? Wh[(c0 + 4) * WS + lc + j] : 0u;
+                            const uint32_t bl0 = lc_ok ? Wl[c0 * WS + lc + j] : 0u, bl1 = lc_ok ? Wl[(c0 + 4) * WS + lc + j] : 0u;
+                            mma_tf32(acc[j], ah, bh0, bh1);
+                            mma_tf32(acc[j], al, bh0, bh1);
+                            mma_tf32(acc[j], ah, bl0, bl1);
+                        }
+                    }
+                }
+                const int r0 = trow + mt * 16 + g, r1 = r0 + 8;
+                auto fin = [&](float a0, float a1, float a2, float a3, const float4& b4, const float4& xv) {
+                    float4 y = make_float4(alpha * (a0 + b4.x), alpha * (a1 + b4.y), alpha * (a2 + b4.z), alpha * (a3 + b4.w));
+                    y.x = fmaf(beta, xv.x, y.x); y.y = fmaf(beta, xv.y, y.y); y.z = fmaf(beta, xv.z, y.z); y.w = fmaf(beta, xv.w, y.w);
+                    return y;
+                };
+                if (r0 < n) {
+                    if (o0) stg4_stream(Out + (size_t)r0 * ldo + oc, fin(acc[0][0], acc[1][0], acc[2][0], acc[3][0], b4a, x[mt][0]));
+                    if (o1) stg4_stream(Out + (size_t)r0 * ldo + oc1, fin(acc[0][1], acc[1][1], acc[2][1], acc[3][1], b4b, x[mt][1]));
+                }
+                if (r1 < n) {
+                    if (o0) stg4_stream(Out + (size_t)r1 * ldo + oc, fin(acc[0][2], acc[1][2], acc[2][2], acc[3][2], b4a, x[mt][2]));
+                    if (o1) stg4_stream(Out + (size_t)r1 * ldo + oc1, fin(acc[0][3], acc[1][3], acc[2][3], acc[3][3], b4b, x[mt][3]));
+                }
+                prefetch(k + 1, mt);                            // refill the registers this m-tile released
+            }
+            if (k + 2 < my_tiles) named_arrive(kEmpty + b, 512);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4-mma: G[c, k] = sum_i H[i, c] A[i, k]  (+ colsum, dot) with M = c, N = k (columns of A), K = rows.
 // CTA = 8 warps = 8 column blocks of 32; every warp sweeps ALL rows of the CTA's tiles for its block, so
 // no cross-warp reduction is needed.  Per 128-row tile the products are accumulated by the tensor core,
@@ -1019,6 +1167,20 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
     if (n == 0) return GCA_OK;
     if constexpr (R == 16 || R == 32) {
         if (tc_enabled()) {
+            static const int use_ws = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && e[0] == 'm') ? 0 : 1; }();
+            const size_t smem_ws = sizeof(uint32_t) * ((size_t)2 * R * (d + 1) + (size_t)4 * kTileRows * (R + 4));
+            if (use_ws && Out && d <= 256 && n >= 4 * kTileRows && smem_ws <= 200 * 1024) {
+                GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR>, smem_ws));
+                const int ntiles_w = (n + kTileRows - 1) / kTileRows;
+                const int grid_w = ntiles_w < num_sms() ? ntiles_w : num_sms();
+                {
+                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                    k_hop_expand_ws<R, W_IS_DR><<<grid_w, 512, smem_ws, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
+                                                                               alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+                }
+                GCA_LAUNCH_OK();
+                return GCA_OK;
+            }
             const size_t smem_m = sizeof(uint32_t) * ((size_t)2 * R * (d + 1) + (size_t)2 * kTileRows * (R + 4));
             if (smem_m <= 100 * 1024) {
                 GCA_TRY(set_smem(k_hop_expand_mma<R, W_IS_DR>, smem_m));
