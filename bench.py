@@ -87,7 +87,8 @@ def algorithmic_bytes(n, e_prime, d, r):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region and an identical
+    1 s continuation of it run (the timed region alone is a few tens of ms)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -97,7 +98,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -237,6 +238,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_step = t0.elapsed_time(t1) / args.steps
     launches = lib.gca_launch_count() - l0
+    # keep the GPU under the same load for ~1 s so nvidia-smi (100 ms period) sees the clocks of this kernel mix
+    t_end = time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
     clocks = sampler.stop()
 
     # ---- per-kernel device times (CUDA events on the launching stream, inside libgca) ----

@@ -57,20 +57,19 @@ __host__ __device__ inline ScratchLayout scratch_layout(int d, int r) {
 template <int R>
 __device__ __forceinline__ float4 gather_rows(const float* __restrict__ F, const int* __restrict__ colidx,
                                               int beg, int end, int stride, int sub) {
+    // Batches of 8 neighbours: all 8 index loads are issued together, then all 8 row loads, so a row of
+    // degree <= 8 costs two dependent memory round trips instead of four.  Missing slots add +0 (exact).
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int e = beg;
-    for (; e + 3 * stride < end; e += 4 * stride) {
-        const int j0 = __ldg(colidx + e), j1 = __ldg(colidx + e + stride);
-        const int j2 = __ldg(colidx + e + 2 * stride), j3 = __ldg(colidx + e + 3 * stride);
-        const float4 v0 = ldg4(F + (size_t)j0 * R + sub * 4);
-        const float4 v1 = ldg4(F + (size_t)j1 * R + sub * 4);
-        const float4 v2 = ldg4(F + (size_t)j2 * R + sub * 4);
-        const float4 v3 = ldg4(F + (size_t)j3 * R + sub * 4);
-        acc = f4_add(acc, v0); acc = f4_add(acc, v1); acc = f4_add(acc, v2); acc = f4_add(acc, v3);
-    }
-    for (; e < end; e += stride) {
-        const int j = __ldg(colidx + e);
-        acc = f4_add(acc, ldg4(F + (size_t)j * R + sub * 4));
+    for (int e = beg; e < end; e += 8 * stride) {
+        int j[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) j[u] = (e + u * stride < end) ? __ldg(colidx + e + u * stride) : -1;
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = (j[u] >= 0) ? ldg4(F + (size_t)j[u] * R + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
     }
     return acc;
 }
@@ -538,8 +537,10 @@ k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict_
             for (int j = 0; j < NT; ++j)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[a_][j][i] = 0.f;
-        for (int kb0 = 0; kb0 < nkb; kb0 += 4) {    // 4 blocks = 8 loads in flight per lane
-            float4 x0[4], x1[4];
+        // software pipeline over batches of 4 column blocks: the 8 loads of batch b+1 are issued before the
+        // tensor-core work of batch b, so 8-16 loads per lane are in flight at all times
+        float4 xa0[4], xa1[4], xb0[4], xb1[4];
+        auto load = [&](float4 (&x0)[4], float4 (&x1)[4], int kb0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (kb0 + u < nkb) {
@@ -547,6 +548,8 @@ k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict_
                     x1[u] = ldg4_stream(p1 + (kb0 + u) * 16);
                 }
             }
+        };
+        auto compute = [&](const float4 (&x0)[4], const float4 (&x1)[4], int kb0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (kb0 + u >= nkb) break;
@@ -568,6 +571,15 @@ k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict_
                         mma_tf32(acc[2][j], ah, q.z, q.w);
                     }
                 }
+            }
+        };
+        load(xa0, xa1, 0);
+        for (int kb0 = 0; kb0 < nkb; kb0 += 8) {
+            if (kb0 + 4 < nkb) load(xb0, xb1, kb0 + 4);
+            compute(xa0, xa1, kb0);
+            if (kb0 + 4 < nkb) {
+                if (kb0 + 8 < nkb) load(xa0, xa1, kb0 + 8);
+                compute(xb0, xb1, kb0 + 4);
             }
         }
         const float sc0 = (r0 < n ? (rowscale ? __ldg(rowscale + r0) : 1.f) : 0.f) * sc_s;
@@ -1012,13 +1024,16 @@ k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ 
 __device__ __forceinline__ float4 sum_partials(const float* __restrict__ part, int np, size_t pitch, int idx4, int lane) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* base = part + (size_t)idx4 * 4;
-    int p = lane;
-    for (; p + 96 < np; p += 128) {              // four independent loads in flight
-        const float4 v0 = ldg4(base + (size_t)p * pitch), v1 = ldg4(base + (size_t)(p + 32) * pitch);
-        const float4 v2 = ldg4(base + (size_t)(p + 64) * pitch), v3 = ldg4(base + (size_t)(p + 96) * pitch);
-        acc = f4_add(acc, f4_add(f4_add(v0, v1), f4_add(v2, v3)));
+    for (int p0 = 0; p0 < np; p0 += 320) {          // 10 predicated loads in flight per lane (np <= 320 -> one round trip)
+        float4 v[10];
+#pragma unroll
+        for (int u = 0; u < 10; ++u) {
+            const int p = p0 + lane + 32 * u;
+            v[u] = p < np ? ldg4(base + (size_t)p * pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 10; ++u) acc = f4_add(acc, v[u]);
     }
-    for (; p < np; p += 32) acc = f4_add(acc, ldg4(base + (size_t)p * pitch));
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
     return acc;
