@@ -279,7 +279,11 @@ def run_ours(args):
                 "alg_bytes_per_launch": per_bytes.get(dom, 0), "ms_per_launch": round(dom_ms, 5),
                 "share_of_step": round(prof[dom]["ms"] / args.steps / kernel_ms, 3)}
     step_gbs = a_min / 1e6 / ms_step
+    # A_gather: every neighbour row fetched once per edge (no cache reuse) - the realistic bound when the r-wide
+    # operand (4 N r bytes) exceeds L2, e.g. products-shaped
+    a_gather = a_min - 16 * n * r + 16 * r * e_prime
     step_roofline = {"alg_bytes_per_step": a_min, "achieved": round(step_gbs, 1), "unit": "GB/s",
+                     "gather_bound_bytes_per_step": a_gather, "achieved_vs_gather_bound": round(a_gather / 1e6 / ms_step, 1),
                      "frac_of_measured_peak": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4),
                      "sum_of_kernel_ms": round(kernel_ms, 5)}
 

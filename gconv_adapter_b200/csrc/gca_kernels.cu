@@ -12,6 +12,8 @@
 // Sparse rows are processed by lane groups (R/4 lanes x 128-bit loads per neighbour row); rows
 // longer than kLongRow are swept by the whole warp.  All reductions have a fixed order.
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "gca_common.cuh"
 
@@ -1108,9 +1110,18 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
 // ------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------
+// Opt in to > 48 KB of dynamic shared memory once per (kernel, size high-water mark), not on every launch.
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) GCA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (bytes <= 48 * 1024) return GCA_OK;
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> done;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return GCA_OK;
+    GCA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
     return GCA_OK;
 }
 

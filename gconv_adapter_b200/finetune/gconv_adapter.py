@@ -34,8 +34,30 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_SIZE_CACHE: dict = {}
+
+
+def _sizes(lib, n: int, d: int, r: int):
+    """(forward workspace bytes, backward workspace bytes) - cached, the C calls are pure functions."""
+    key = (n, d, r)
+    hit = _SIZE_CACHE.get(key)
+    if hit is None:
+        hit = (lib.gca_forward_workspace_bytes(n, d, r), lib.gca_backward_workspace_bytes(n, d, r))
+        if len(_SIZE_CACHE) > 256:
+            _SIZE_CACHE.clear()
+        _SIZE_CACHE[key] = hit
+    return hit
+
+
+def _align(nbytes: int) -> int:
+    return (nbytes + 255) // 256 * 256
+
+
 class _GConvAdapterFunction(torch.autograd.Function):
-    """Y = s * (Ahat act(Ahat X Wd^T + bd) Wu^T + bu [+ X]) and its gradients, one graph handle."""
+    """Y = s * (Ahat act(Ahat X Wd^T + bd) Wu^T + bu [+ X]) and its gradients, one graph handle.
+
+    The host side is kept thin on purpose (the small configs are launch-bound): one device allocation per
+    direction, carved into the tensors the kernels need, and one C call."""
 
     @staticmethod
     def forward(ctx, x, w_down, b_down, w_up, b_up, scalar, graph: GraphStructure, act: int, skip: bool):
@@ -43,59 +65,74 @@ class _GConvAdapterFunction(torch.autograd.Function):
         n, d = x.shape
         r = w_down.shape[0]
         dev = x.device
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            w_down, b_down, w_up, b_up = (t.contiguous() for t in (w_down, b_down, w_up, b_up))
-            y = torch.empty((n, d), dtype=torch.float32, device=dev)
-            zp = torch.empty((n, r), dtype=torch.float32, device=dev)
-            h2 = torch.empty((n, r), dtype=torch.float32, device=dev)
-            h1 = torch.empty((n, r), dtype=torch.float32, device=dev) if act == _cabi.ACT["silu"] else None
-            ws = torch.empty(lib.gca_forward_workspace_bytes(n, d, r), dtype=torch.uint8, device=dev)
-            _cabi.check(lib.gca_forward(graph.handle, x.data_ptr(), x.stride(0), w_down.data_ptr(), b_down.data_ptr(),
-                                        w_up.data_ptr(), b_up.data_ptr(), _ptr(scalar), act, int(skip), ws.data_ptr(),
-                                        zp.data_ptr(), _ptr(h1), h2.data_ptr(), y.data_ptr(), y.stride(0), d, r,
-                                        stream), "gca_forward")
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        if not w_down.is_contiguous():
+            w_down = w_down.contiguous()
+        if not w_up.is_contiguous():
+            w_up = w_up.contiguous()
+        b_down, b_up = b_down.contiguous(), b_up.contiguous()
+        silu = act == _cabi.ACT["silu"]
+        y = torch.empty((n, d), dtype=torch.float32, device=dev)
+        # one allocation: [Z' | H2 | (H1) | projection scratch]
+        rw = _align(4 * max(n, 1) * r)
+        ws_bytes = _sizes(lib, n, d, r)[0]
+        buf = torch.empty((3 if silu else 2) * rw + ws_bytes, dtype=torch.uint8, device=dev)
+        base = buf.data_ptr()
+        zp_ptr, h2_ptr = base, base + rw
+        h1_ptr = base + 2 * rw if silu else None
+        ws_ptr = base + (3 if silu else 2) * rw
+        _cabi.check(lib.gca_forward(graph.handle, x.data_ptr(), x.stride(0), w_down.data_ptr(), b_down.data_ptr(),
+                                    w_up.data_ptr(), b_up.data_ptr(), _ptr(scalar), act, int(skip), ws_ptr,
+                                    zp_ptr, h1_ptr, h2_ptr, y.data_ptr(), y.stride(0), d, r, stream), "gca_forward")
         ctx.graph, ctx.act, ctx.skip = graph, act, skip
         ctx.has_scalar = scalar is not None
-        ctx.has_h1 = h1 is not None
-        saved = [x, w_down, w_up, b_up, zp, h2]
+        ctx.silu, ctx.rw = silu, rw
+        saved = [x, w_down, w_up, b_up, buf]
         if scalar is not None:
             saved.append(scalar)
-        if h1 is not None:
-            saved.append(h1)
         ctx.save_for_backward(*saved)
         if DEBUG_KEEP_SAVED:
-            LAST_SAVED.update(zp=zp, h2=h2, h1=h1)
+            nr = n * r
+            f = buf[:(3 if silu else 2) * rw].view(torch.float32)
+            LAST_SAVED.update(zp=f[:nr].view(n, r), h2=f[rw // 4:rw // 4 + nr].view(n, r),
+                              h1=f[2 * rw // 4:2 * rw // 4 + nr].view(n, r) if silu else None)
         return y
 
     @staticmethod
     def backward(ctx, g_y):
         lib = _cabi.load()
-        saved = list(ctx.saved_tensors)
-        x, w_down, w_up, b_up, zp, h2 = saved[:6]
-        rest = saved[6:]
-        scalar = rest.pop(0) if ctx.has_scalar else None
-        h1 = rest.pop(0) if ctx.has_h1 else None
+        saved = ctx.saved_tensors
+        x, w_down, w_up, b_up, buf = saved[:5]
+        scalar = saved[5] if ctx.has_scalar else None
         n, d = x.shape
         r = w_down.shape[0]
         dev = x.device
         if g_y.stride(-1) != 1 or g_y.stride(0) % 4 != 0 or g_y.data_ptr() % 16 != 0:
             g_y = g_y.contiguous()
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            need_x = ctx.needs_input_grad[0]
-            g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
-            g_wd = torch.empty_like(w_down)
-            g_bd = torch.empty((r,), dtype=torch.float32, device=dev)
-            g_wu = torch.empty_like(w_up)
-            g_bu = torch.empty((d,), dtype=torch.float32, device=dev)
-            g_s = torch.empty((1,), dtype=torch.float32, device=dev) if scalar is not None else None
-            ws = torch.empty(lib.gca_backward_workspace_bytes(n, d, r), dtype=torch.uint8, device=dev)
-            _cabi.check(lib.gca_backward(ctx.graph.handle, g_y.data_ptr(), g_y.stride(0), x.data_ptr(), x.stride(0),
-                                         zp.data_ptr(), _ptr(h1), h2.data_ptr(), w_down.data_ptr(), w_up.data_ptr(),
-                                         b_up.data_ptr(), _ptr(scalar), ctx.act, int(ctx.skip), ws.data_ptr(),
-                                         _ptr(g_x), g_x.stride(0) if need_x else d, g_wd.data_ptr(), g_bd.data_ptr(),
-                                         g_wu.data_ptr(), g_bu.data_ptr(), _ptr(g_s), d, r, stream), "gca_backward")
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        rw = ctx.rw
+        base = buf.data_ptr()
+        zp_ptr, h2_ptr = base, base + rw
+        h1_ptr = base + 2 * rw if ctx.silu else None
+        need_x = ctx.needs_input_grad[0]
+        g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
+        # parameter gradients in one allocation: [gWd | gWu | gbu | gbd | gs]
+        flat = torch.empty(2 * d * r + d + r + 1, dtype=torch.float32, device=dev)
+        g_wd = flat[0:d * r].view(r, d)
+        g_wu = flat[d * r:2 * d * r].view(d, r)
+        g_bu = flat[2 * d * r:2 * d * r + d]
+        g_bd = flat[2 * d * r + d:2 * d * r + d + r]
+        g_s = flat[2 * d * r + d + r:] if scalar is not None else None
+        ws = torch.empty(_sizes(lib, n, d, r)[1], dtype=torch.uint8, device=dev)
+        _cabi.check(lib.gca_backward(ctx.graph.handle, g_y.data_ptr(), g_y.stride(0), x.data_ptr(), x.stride(0),
+                                     zp_ptr, h1_ptr, h2_ptr, w_down.data_ptr(), w_up.data_ptr(),
+                                     b_up.data_ptr(), _ptr(scalar), ctx.act, int(ctx.skip), ws.data_ptr(),
+                                     _ptr(g_x), g_x.stride(0) if need_x else d, g_wd.data_ptr(), g_bd.data_ptr(),
+                                     g_wu.data_ptr(), g_bu.data_ptr(), _ptr(g_s), d, r, stream), "gca_backward")
         return g_x, g_wd, g_bd, g_wu, g_bu, g_s, None, None, None
 
 

@@ -120,9 +120,10 @@ class _PartitionedFunction(torch.autograd.Function):
         r = w_down.shape[0]
         dev = x.device
         w_down, b_down, w_up, b_up = (t.contiguous() for t in (w_down, b_down, w_up, b_up))
-        # padded rows (beyond N) of the gathered buffers are never referenced by any neighbour id
-        p_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
-        z_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
+        # padded rows (beyond N) of the gathered buffers are never referenced by any neighbour id, so the
+        # buffers need no initialisation: every real row is written by its owner's kernel or by the all-gather
+        p_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
+        z_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
         h2 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
         h1 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev) if act == _cabi.ACT["silu"] else None
         y = torch.empty((n, d), dtype=torch.float32, device=dev)
@@ -156,8 +157,8 @@ class _PartitionedFunction(torch.autograd.Function):
         backend, graph, group = ctx.backend, ctx.graph, ctx.group
         dev = x.device
         g_y = g_y.contiguous()
-        gh2_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
-        gh1_full = torch.zeros((world * s, r), dtype=torch.float32, device=dev)
+        gh2_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
+        gh1_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
         gp = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
         need_x = ctx.needs_input_grad[0]
         g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
