@@ -77,6 +77,7 @@ def algorithmic_bytes(n, e_prime, d, r):
         "hop_expand_fwd": 2 * nr + idx + dis + 2 * nd,  # Z' -> H2 ; X -> Y
         "project_bwd": nd + nr + dis,                 # gY -> gH2'
         "wgrad_up": nd + nr,                          # gY, H2 -> gWu partials
+        "bwd_up_fused": nd + 2 * nr + dis,            # gY (once) -> gH2' and gWu partials (project_bwd + wgrad_up)
         "hop_bwd": 3 * nr + idx + dis,                # gH2', Z' -> gH1'
         "hop_expand_bwd": 2 * nr + idx + dis + 2 * nd,  # gH1' -> gP ; gY -> gX
         "wgrad_down": 2 * nd + nr,                    # X, gY(dot), gP -> gWd partials

@@ -499,11 +499,11 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // (k-step, n-tile).  Products go to 2 accumulator sets (alternating 16-column blocks) + 1 for the lo terms.
 // ------------------------------------------------------------------------------------------
 template <int R, bool W_IS_RD>
-__global__ void __launch_bounds__(256, 2)
-k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ rowscale,
-              const float* __restrict__ scalar, float* __restrict__ out, int n, int d) {
+__device__ __forceinline__ void project_mma_body(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
+                                                 const float* __restrict__ rowscale, const float* __restrict__ scalar,
+                                                 float* __restrict__ out, int n, int d, int bid, int nblocks,
+                                                 uint32_t* smem_u) {
     constexpr int NT = R / 8;                       // n-tiles
-    extern __shared__ __align__(16) uint32_t smem_u[];
     // Wq[kb][s][nt][g][t] = uint4 {hi(k0,c), hi(k1,c), lo(k0,c), lo(k1,c)}, k0 = kb*16+4t+2s, k1 = k0+1, c = nt*8+g
     // (lane = 4g + t reads consecutive 16-byte slots: conflict-free LDS.128)
     uint4* Wq = reinterpret_cast<uint4*>(smem_u);
@@ -527,7 +527,7 @@ k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict_
     const int g = lane >> 2, t = lane & 3;
     const float sc_s = scalar ? __ldg(scalar) : 1.f;
     const int nmt = (n + 15) / 16;                  // 16-row m-tiles
-    const int wglobal = blockIdx.x * 8 + warp, wtotal = gridDim.x * 8;
+    const int wglobal = bid * 8 + warp, wtotal = nblocks * 8;
     for (int mt = wglobal; mt < nmt; mt += wtotal) {
         const int r0 = mt * 16 + g, r1 = r0 + 8;
         const float* p0 = A + (size_t)min(r0, n - 1) * lda + 4 * t;
@@ -595,6 +595,14 @@ k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict_
             if (r1 < n) *reinterpret_cast<float2*>(out + (size_t)r1 * R + j * 8 + 2 * t) = make_float2(v[2] * sc1, v[3] * sc1);
         }
     }
+}
+
+template <int R, bool W_IS_RD>
+__global__ void __launch_bounds__(256, 2)
+k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ rowscale,
+              const float* __restrict__ scalar, float* __restrict__ out, int n, int d) {
+    extern __shared__ __align__(16) uint32_t smem_dyn[];
+    project_mma_body<R, W_IS_RD>(A, lda, W, rowscale, scalar, out, n, d, blockIdx.x, gridDim.x, smem_dyn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -887,10 +895,10 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 constexpr int kMmaRows = 128;
 
 template <int R>
-__global__ void __launch_bounds__(256, R == 16 ? 2 : 1)
-k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, const float* __restrict__ B, int64_t ldb,
-            float* __restrict__ partG, float* __restrict__ partCol, float* __restrict__ partDot, int* header, int header_slot,
-            int n, int d, int col_base) {
+__device__ __forceinline__ void wgrad_mma_body(const float* __restrict__ A, int64_t lda, const float* __restrict__ H,
+                                               const float* __restrict__ B, int64_t ldb, float* __restrict__ partG,
+                                               float* __restrict__ partCol, float* __restrict__ partDot, int* header,
+                                               int header_slot, int n, int d, int col_base, int bid, int nblocks) {
     constexpr int MT = R / 16;            // m-tiles (16 c's each)
     constexpr int RS = R + 8;             // padded row stride of the H tile (conflict-free A-fragment loads)
     __shared__ __align__(16) uint32_t Hh[kMmaRows * RS];
@@ -911,7 +919,7 @@ k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ 
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     float dot = 0.f;
     const int ntiles = (n + kMmaRows - 1) / kMmaRows;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = bid; tile < ntiles; tile += nblocks) {
         const int row0 = tile * kMmaRows;
         const int rows = min(kMmaRows, n - row0);
         __syncthreads();
@@ -984,7 +992,7 @@ k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ 
                 for (int i = 0; i < 4; ++i) run[m][j][i] += acc[m][j][i];
     }
     // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns cb+8t .. cb+8t+7 ----
-    float* pg = partG + (size_t)blockIdx.x * R * d;
+    float* pg = partG + (size_t)bid * R * d;
     const int oc = cb + 8 * t;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
@@ -1003,7 +1011,7 @@ k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ 
     // column sums: add the 4 row-lanes (t) of every column quad
     csum = f4_add(csum, f4_shfl_xor(csum, 1));
     csum = f4_add(csum, f4_shfl_xor(csum, 2));
-    if (partCol && t == 0 && col_ok) *reinterpret_cast<float4*>(partCol + (size_t)blockIdx.x * d + col) = csum;
+    if (partCol && t == 0 && col_ok) *reinterpret_cast<float4*>(partCol + (size_t)bid * d + col) = csum;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
     if (lane == 0) s_dot[warp] = dot;
@@ -1012,32 +1020,53 @@ k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ 
         if (partDot) {
             float tsum = 0.f;
             for (int w_ = 0; w_ < 8; ++w_) tsum += s_dot[w_];
-            if (col_base == 0) partDot[blockIdx.x] = tsum; else partDot[blockIdx.x] += tsum;   // launches are stream-ordered
+            if (col_base == 0) partDot[bid] = tsum; else partDot[bid] += tsum;   // launches are stream-ordered
         }
-        if (blockIdx.x == 0) header[header_slot] = gridDim.x;
+        if (bid == 0) header[header_slot] = nblocks;
     }
 }
 
+template <int R>
+__global__ void __launch_bounds__(256, R == 16 ? 2 : 1)
+k_wgrad_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ H, const float* __restrict__ B, int64_t ldb,
+            float* __restrict__ partG, float* __restrict__ partCol, float* __restrict__ partDot, int* header, int header_slot,
+            int n, int d, int col_base) {
+    wgrad_mma_body<R>(A, lda, H, B, ldb, partG, partCol, partDot, header, header_slot, n, d, col_base, blockIdx.x, gridDim.x);
+}
+
+// Horizontal fusion of the two kernels that stream gY in the backward (gH2' = gY Wu and gWu = gY^T H2): even
+// CTAs run the projection, odd CTAs the weight gradient, both walking the same 128-row tiles in the same order,
+// so whichever role touches a tile second finds it in L2 - gY crosses HBM once - and the two roles' tensor-core
+// and memory phases overlap on every SM.
+template <int R>
+__global__ void __launch_bounds__(256, R == 16 ? 2 : 1)
+k_bwd_up_fused(const float* __restrict__ gY, int64_t ldg, const float* __restrict__ Wu, const float* __restrict__ dis,
+               const float* __restrict__ scalar, float* __restrict__ gH2p, const float* __restrict__ H2,
+               float* __restrict__ partG, float* __restrict__ partCol, int* header, int n, int d) {
+    extern __shared__ __align__(16) uint32_t smem_dyn[];
+    const int role = blockIdx.x & 1, vb = blockIdx.x >> 1, vg = gridDim.x >> 1;
+    if (role == 0) project_mma_body<R, false>(gY, ldg, Wu, dis, scalar, gH2p, n, d, vb, vg, smem_dyn);
+    else wgrad_mma_body<R>(gY, ldg, H2, nullptr, 0, partG, partCol, nullptr, header, 0, n, d, 0, vb, vg);
+}
+
 // ------------------------------------------------------------------------------------------
-// K6: second-stage reduction of the per-CTA partials, fixed order.  One warp per column quad: lane l
-// sums partials l, l+32, ... (independent loads, one round trip), a 5-step butterfly adds the 32 lane
-// sums.  The last CTA to finish adds up the gscalar pieces.
+// K6: second-stage reduction of the per-CTA partials, fixed order.  A job = one block of 32 consecutive
+// column quads of one partial array (512 contiguous bytes per partial row: coalesced).  The 8 warps of a CTA
+// split the partial rows (warp w sums rows w, w+8, ... with 8 loads in flight), their 8 sums are added in warp
+// order through shared memory, and warp 0 writes the result.  The last CTA to finish adds up the gscalar pieces.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 sum_partials(const float* __restrict__ part, int np, size_t pitch, int idx4, int lane) {
+__device__ __forceinline__ float4 sum_rows_strided(const float* __restrict__ base, int np, size_t pitch, int first, bool ok) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* base = part + (size_t)idx4 * 4;
-    for (int p0 = 0; p0 < np; p0 += 320) {          // 10 predicated loads in flight per lane (np <= 320 -> one round trip)
-        float4 v[10];
+    if (!ok) return acc;
+    int p = first;
+    for (; p + 56 < np; p += 64) {
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 10; ++u) {
-            const int p = p0 + lane + 32 * u;
-            v[u] = p < np ? ldg4(base + (size_t)p * pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int u = 0; u < 8; ++u) v[u] = ldg4(base + (size_t)(p + 8 * u) * pitch);
 #pragma unroll
-        for (int u = 0; u < 10; ++u) acc = f4_add(acc, v[u]);
+        for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
     }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
+    for (; p < np; p += 8) acc = f4_add(acc, ldg4(base + (size_t)p * pitch));
     return acc;
 }
 
@@ -1046,46 +1075,58 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
            const float* __restrict__ partDot, const float* __restrict__ partBd, float* gsp, int* header,
            const float* __restrict__ Wu, const float* __restrict__ bu, const float* __restrict__ scalar, int skip,
            float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar, int d, int r) {
+    __shared__ float4 s_part[8][32];
+    __shared__ float s_red[256];
+    __shared__ int s_last;
     const int pu = header[0], pd = header[1], pb = header[2];
     const float s = scalar ? __ldg(scalar) : 1.f;
     const int rd4 = (r * d) >> 2, d4 = d >> 2, r4 = r >> 2;
-    const int lane = threadIdx.x & 31;
-    const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wtotal = gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int jb_g = (rd4 + 31) / 32, jb_c = (d4 + 31) / 32;
+    const int njobs = 2 * jb_g + jb_c + 1;             // [gu blocks][gd blocks][colsum blocks][bd]
     float gs = 0.f;
-    for (int q = wglobal; q < rd4; q += wtotal) {                        // warp-uniform
-        const float4 gu = sum_partials(partGu, pu, (size_t)r * d, q, lane);
-        float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gWd) gd = sum_partials(partGd, pd, (size_t)r * d, q, lane);
-        if (lane == 0) {
-            const int c = (q * 4) / d, k = q * 4 - c * d;
-            const float g4[4] = {gu.x, gu.y, gu.z, gu.w};
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        int kind, blk;
+        if (job < jb_g) { kind = 0; blk = job; }
+        else if (job < 2 * jb_g) { kind = 1; blk = job - jb_g; }
+        else if (job < 2 * jb_g + jb_c) { kind = 2; blk = job - 2 * jb_g; }
+        else { kind = 3; blk = 0; }
+        const float* part = kind == 0 ? partGu : kind == 1 ? partGd : kind == 2 ? partCol : partBd;
+        const int np = kind == 0 ? pu : kind == 1 ? pd : kind == 2 ? pu : pb;
+        const int nq = kind <= 1 ? rd4 : kind == 2 ? d4 : r4;
+        const size_t pitch = kind <= 1 ? (size_t)r * d : kind == 2 ? (size_t)d : (size_t)r;
+        const int q = blk * 32 + lane;
+        const bool ok = q < nq && !(kind == 1 && !gWd) && !(kind == 3 && !gbd);
+        const float4 mine = sum_rows_strided(part + (size_t)q * 4, np, pitch, warp, ok);
+        __syncthreads();
+        s_part[warp][lane] = mine;
+        __syncthreads();
+        if (warp == 0 && ok) {
+            float4 t = s_part[0][lane];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (gWu) gWu[(size_t)(k + j) * r + c] = s * g4[j];
-                gs = fmaf(g4[j], __ldg(Wu + (size_t)(k + j) * r + c), gs);
+            for (int w = 1; w < 8; ++w) t = f4_add(t, s_part[w][lane]);
+            if (kind == 0) {
+                const int c = (q * 4) / d, k = q * 4 - c * d;
+                const float g4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (gWu) gWu[(size_t)(k + j) * r + c] = s * g4[j];
+                    gs = fmaf(g4[j], __ldg(Wu + (size_t)(k + j) * r + c), gs);
+                }
+            } else if (kind == 1) {
+                *reinterpret_cast<float4*>(gWd + (size_t)q * 4) = t;
+            } else if (kind == 2) {
+                if (gbu) *reinterpret_cast<float4*>(gbu + q * 4) = f4_scale(t, s);
+                const float4 b = ldg4(bu + q * 4);
+                gs = fmaf(t.x, b.x, fmaf(t.y, b.y, fmaf(t.z, b.z, fmaf(t.w, b.w, gs))));
+            } else {
+                *reinterpret_cast<float4*>(gbd + q * 4) = t;
             }
-            if (gWd) *reinterpret_cast<float4*>(gWd + (size_t)q * 4) = gd;
-        }
-    }
-    for (int q = wglobal; q < d4; q += wtotal) {
-        const float4 cs = sum_partials(partCol, pu, (size_t)d, q, lane);
-        if (lane == 0) {
-            if (gbu) *reinterpret_cast<float4*>(gbu + q * 4) = f4_scale(cs, s);
-            const float4 b = ldg4(bu + q * 4);
-            gs = fmaf(cs.x, b.x, fmaf(cs.y, b.y, fmaf(cs.z, b.z, fmaf(cs.w, b.w, gs))));
-        }
-    }
-    if (gbd) {
-        for (int q = wglobal; q < r4; q += wtotal) {
-            const float4 t = sum_partials(partBd, pb, (size_t)r, q, lane);
-            if (lane == 0) *reinterpret_cast<float4*>(gbd + q * 4) = t;
         }
     }
     if (!gscalar) return;
     if (skip && blockIdx.x == 0)
         for (int p = threadIdx.x; p < pd; p += blockDim.x) gs += partDot[p];
-    __shared__ float s_red[256];
-    __shared__ int s_last;
     s_red[threadIdx.x] = gs;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -1112,8 +1153,8 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
 // ------------------------------------------------------------------------------------------
 // Opt in to > 48 KB of dynamic shared memory once per (kernel, size high-water mark), not on every launch.
 template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return GCA_OK;
+int set_smem(K kernel, size_t bytes, bool has_static_smem = false) {
+    if (bytes <= 48 * 1024 && !has_static_smem) return GCA_OK;   // static + dynamic > 48 KB needs the opt-in too
     static std::mutex mu;
     static std::unordered_map<const void*, size_t> done;
     const void* key = reinterpret_cast<const void*>(kernel);
@@ -1353,6 +1394,23 @@ Scratch scratch_ptrs(void* scratch, int d, int r) {
 template <int R>
 int bwd_up_impl(const gca_graph* g, const float* gY, int64_t ldg, const float* H2, const float* Wu, const float* scalar,
                 float* gH2p, const Scratch& S, int n, int d, cudaStream_t st) {
+    if constexpr (R == 16 || R == 32) {
+        // measured: the fused launch takes exactly the sum of the two kernels (110 us at arxiv shape: the step is
+        // bound by tensor/LSU/latency, not by HBM traffic), so it is opt-in (GCA_BWD_UP=fused).
+        static const int no_fuse = [] { const char* e = getenv("GCA_BWD_UP"); return (e && e[0] == 'f') ? 0 : 1; }();
+        const size_t smem_m = sizeof(uint4) * (size_t)(d / 16) * 2 * 4 * (R / 8) * 8;
+        if (tc_enabled() && !no_fuse && d % 16 == 0 && d <= 256 && n >= 4 * kMmaRows && smem_m <= 64 * 1024) {
+            GCA_TRY(set_smem(k_bwd_up_fused<R>, smem_m, true));
+            const int ntiles = (n + kMmaRows - 1) / kMmaRows;
+            const int vg = ntiles < num_sms() ? ntiles : num_sms();
+            {
+                ProfScope ps("bwd_up_fused", st);
+                k_bwd_up_fused<R><<<2 * vg, 256, smem_m, st>>>(gY, ldg, Wu, g->dis, scalar, gH2p, H2, S.gu, S.col, S.header, n, d);
+            }
+            GCA_LAUNCH_OK();
+            return GCA_OK;
+        }
+    }
     GCA_TRY((launch_project<R, false>(gY, ldg, Wu, g->dis, scalar, gH2p, n, d, st)));
     return launch_wgrad<R>(gY, ldg, H2, nullptr, 0, S.gu, S.col, nullptr, S.header, 0, n, d, st);
 }
@@ -1415,8 +1473,8 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
                                 gca_stream_t stream) {
     if (!scratch || !Wu || !bu || d <= 0 || r <= 0) return GCA_ERR_INVALID_ARG;
     const Scratch S = scratch_ptrs(const_cast<void*>(scratch), d, r);
-    int grid = ((r * d) / 4 + 7) / 8;                // one warp per column quad, 8 warps per CTA
-    if (grid < 1) grid = 1;
+    const int rd4 = (r * d) / 4;
+    int grid = 2 * ((rd4 + 31) / 32) + (d / 4 + 31) / 32 + 1;   // one CTA per job
     if (grid > kMaxFin) grid = kMaxFin;
     {
         ProfScope ps("finalize", static_cast<cudaStream_t>(stream));
