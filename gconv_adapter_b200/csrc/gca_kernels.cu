@@ -1058,15 +1058,14 @@ k_bwd_up_fused(const float* __restrict__ gY, int64_t ldg, const float* __restric
 __device__ __forceinline__ float4 sum_rows_strided(const float* __restrict__ base, int np, size_t pitch, int first, bool ok) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!ok) return acc;
-    int p = first;
-    for (; p + 56 < np; p += 64) {
+    for (int p = first; p < np; p += 64) {          // 8 predicated loads in flight, no serial tail
         float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ldg4(base + (size_t)(p + 8 * u) * pitch);
+        for (int u = 0; u < 8; ++u)
+            v[u] = (p + 8 * u < np) ? ldg4(base + (size_t)(p + 8 * u) * pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
     }
-    for (; p < np; p += 8) acc = f4_add(acc, ldg4(base + (size_t)p * pitch));
     return acc;
 }
 
