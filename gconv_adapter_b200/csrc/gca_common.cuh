@@ -60,6 +60,30 @@ inline int record(cudaError_t e) {
         GCA_CUDA(cudaGetLastError());                   \
     } while (0)
 
+// Programmatic dependent launch (PDL): kernels of one forward / backward are chained on a stream; with the
+// launch attribute below the next kernel's CTAs may start (and run their prologue: weight staging into shared
+// memory) while the previous kernel drains.  pdl_wait() blocks until the previous kernel has completed and its
+// writes are visible - it MUST precede the first access to anything a neighbouring kernel reads or writes;
+// pdl_trigger() lets the dependent kernel start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kWarp = 32;
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }

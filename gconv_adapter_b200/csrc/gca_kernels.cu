@@ -216,6 +216,8 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPG, grp = lane / LPG;
     const int wglobal = blockIdx.x * (blockDim.x >> 5) + warp, wtotal = gridDim.x * (blockDim.x >> 5);
+    pdl_wait();
+    pdl_trigger();
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!BWD && bias) b4 = ldg4(bias + sub * 4);
     float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -504,6 +506,9 @@ __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, in
                                                  float* __restrict__ out, int n, int d, int bid, int nblocks,
                                                  uint32_t* smem_u) {
     constexpr int NT = R / 8;                       // n-tiles
+    // The projections are the first kernels of gca_forward / gca_backward: what precedes them on the stream is
+    // not ours (an optimizer step may just have written W), so they wait before touching anything.
+    pdl_wait();
     // Wq[kb][s][nt][g][t] = uint4 {hi(k0,c), hi(k1,c), lo(k0,c), lo(k1,c)}, k0 = kb*16+4t+2s, k1 = k0+1, c = nt*8+g
     // (lane = 4g + t reads consecutive 16-byte slots: conflict-free LDS.128)
     uint4* Wq = reinterpret_cast<uint4*>(smem_u);
@@ -523,6 +528,7 @@ __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, in
         Wq[idx] = q;
     }
     __syncthreads();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const float sc_s = scalar ? __ldg(scalar) : 1.f;
@@ -775,6 +781,8 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         Wl[c * WS + k] = lo;
     }
     __syncthreads();
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ntiles = (n + kTileRows - 1) / kTileRows;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -901,6 +909,8 @@ __device__ __forceinline__ void wgrad_mma_body(const float* __restrict__ A, int6
                                                int header_slot, int n, int d, int col_base, int bid, int nblocks) {
     constexpr int MT = R / 16;            // m-tiles (16 c's each)
     constexpr int RS = R + 8;             // padded row stride of the H tile (conflict-free A-fragment loads)
+    pdl_wait();
+    pdl_trigger();
     __shared__ __align__(16) uint32_t Hh[kMmaRows * RS];
     __shared__ __align__(16) uint32_t Hl[kMmaRows * RS];
     __shared__ float s_dot[8];
@@ -1077,6 +1087,7 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
     __shared__ float4 s_part[8][32];
     __shared__ float s_red[256];
     __shared__ int s_last;
+    pdl_wait();
     const int pu = header[0], pd = header[1], pb = header[2];
     const float s = scalar ? __ldg(scalar) : 1.f;
     const int rd4 = (r * d) >> 2, d4 = d >> 2, r4 = r >> 2;
@@ -1186,7 +1197,7 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
                     if (grid_m > 2 * num_sms()) grid_m = 2 * num_sms();
                     {
                         ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
-                        k_project_mma<R, W_IS_RD><<<grid_m, 256, smem_m, st>>>(A, lda, W, rowscale, scalar, out, n, d);
+                        GCA_CUDA(launch_pdl(k_project_mma<R, W_IS_RD>, dim3(grid_m), dim3(256), smem_m, st, A, lda, W, rowscale, scalar, out, n, d));
                     }
                     GCA_LAUNCH_OK();
                     return GCA_OK;
@@ -1220,7 +1231,7 @@ int launch_hop(const int* rowptr, const int* colidx, const float* dis, const flo
     if (grid < 1) grid = 1;
     {
         ProfScope ps(BWD ? "hop_bwd" : "hop_fwd", st);
-        k_hop<R, BWD><<<grid, 256, 0, st>>>(rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n);
+        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n));
     }
     GCA_LAUNCH_OK();
     return GCA_OK;
@@ -1241,8 +1252,8 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
                 const int grid_w = ntiles_w < num_sms() ? ntiles_w : num_sms();
                 {
                     ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
-                    k_hop_expand_ws<R, W_IS_DR><<<grid_w, 512, smem_ws, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
-                                                                               alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+                    GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR>, dim3(grid_w), dim3(512), smem_ws, st, rowptr, colidx, dis, F, W, bias,
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d));
                 }
                 GCA_LAUNCH_OK();
                 return GCA_OK;
@@ -1287,7 +1298,7 @@ int launch_wgrad(const float* A, int64_t lda, const float* H, const float* B, in
             if (grid > cap) grid = cap;
             for (int col0 = 0; col0 < d; col0 += 256) {
                 ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st);
-                k_wgrad_mma<R><<<grid, 256, 0, st>>>(A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d, col0);
+                GCA_CUDA(launch_pdl(k_wgrad_mma<R>, dim3(grid), dim3(256), 0, st, A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d, col0));
                 count_launch();
             }
             GCA_CUDA(cudaGetLastError());
@@ -1477,8 +1488,8 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
     if (grid > kMaxFin) grid = kMaxFin;
     {
         ProfScope ps("finalize", static_cast<cudaStream_t>(stream));
-        k_finalize<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S.gu, S.col, S.gd, S.dot, S.bd, S.gsp, S.header, Wu, bu,
-                                                                         scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r);
+        GCA_CUDA(launch_pdl(k_finalize, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), S.gu, S.col, S.gd, S.dot, S.bd,
+                            S.gsp, S.header, Wu, bu, scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r));
     }
     GCA_LAUNCH_OK();
     return GCA_OK;

@@ -36,6 +36,16 @@ bool tc_enabled() {
     return cached == 1;
 }
 
+// GCA_DISABLE_PDL=1 launches every kernel fully serialised (A/B runs).
+bool pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GCA_DISABLE_PDL");
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1;
+}
+
 struct ProfEntry { const char* name; cudaEvent_t a, b; };
 static std::atomic<bool> g_prof_on{false};
 static std::mutex g_prof_mu;
