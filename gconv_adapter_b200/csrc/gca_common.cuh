@@ -19,8 +19,21 @@ struct gca_graph {
     float* dis;
     int32_t* cnt;      // [n] counters / fill cursors (forward CSR)
     int32_t* cnt_t;    // [n] counters / fill cursors (transposed CSR)
-    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t
+    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t, [3] hub items, [4] hub items (transpose)
+    // Hub rows (degree > kHubDeg) are cut into work items of kHubChunk neighbours (see gca_graph.cu / k_hub_partials)
+    int32_t* hubitem;      // [n]  first item of a hub row, -1 otherwise          (forward CSR)
+    int32_t* hubitem_t;    // [n]                                                 (transposed CSR)
+    int32_t* item_row;     // [hub_cap] local row of an item
+    int32_t* item_row_t;
+    float* hub_part;       // [hub_cap][64] partial sums of the items (scratch, one stream at a time per handle)
+    int64_t hub_cap;
+    int32_t nitems, nitems_t;   // host copies after gca_graph_validate; -1 = unknown
 };
+
+namespace gca {
+constexpr int kHubDeg = 512;      // rows longer than this take the hub path
+constexpr int kHubChunk = 512;    // neighbours per hub work item (one warp each)
+}
 
 namespace gca {
 

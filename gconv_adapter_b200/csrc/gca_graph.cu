@@ -185,6 +185,47 @@ __device__ void sort_rows_cta(const int* __restrict__ rowptr, int* colidx, int r
     }
 }
 
+// List the hub rows of one CSR in row order (one CTA): hubitem[row] = first work item or -1, item_row[item] = row.
+// Row order makes the item numbering - and with it every partial-sum order - independent of scheduling.
+__device__ void list_hubs(const int* __restrict__ rowptr, int n, int* __restrict__ hubitem, int* __restrict__ item_row,
+                          int* total_out, int* s_warp /*[33]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int row = base + tid;
+        int items = 0;
+        if (row < n) {
+            const int deg = rowptr[row + 1] - rowptr[row];
+            if (deg > kHubDeg) items = (deg + kHubChunk - 1) / kHubChunk;
+        }
+        const int incl = warp_incl_scan(items, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = (lane < nwarps) ? s_warp[lane] : 0;
+            const int wi = warp_incl_scan(w, lane);
+            s_warp[lane] = wi - w;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        if (row < n) {
+            const int first = carry + s_warp[warp] + incl - items;
+            hubitem[row] = items ? first : -1;
+            for (int c = 0; c < items; ++c) item_row[first + c] = row;
+        }
+        carry += s_warp[32];
+        __syncthreads();
+    }
+    if (tid == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(1024) k0_hubs(const int* rowptr, const int* rowptr_t, int n, int* hubitem, int* hubitem_t,
+                                                int* item_row, int* item_row_t, int* flags) {
+    __shared__ int s_warp[33];
+    if (blockIdx.x == 0) list_hubs(rowptr, n, hubitem, item_row, &flags[3], s_warp);
+    else list_hubs(rowptr_t, n, hubitem_t, item_row_t, &flags[4], s_warp);
+}
+
 // ---------------- multi-launch build ---------------------------------------------------------
 __global__ void k0_count(const int64_t* src, const int64_t* dst, int64_t E, int N, int rb, int re,
                          int normalize, int* cnt, int* cnt_t, int* flags) {
@@ -221,13 +262,14 @@ __global__ void __launch_bounds__(256) k0_sort(const int* rowptr, int* colidx, c
 __global__ void __launch_bounds__(1024) k0_build_small(const int64_t* src, const int64_t* dst, int64_t E, int N,
                                                        int rb, int re, int normalize, int* cnt, int* cnt_t,
                                                        int* rowptr, int* rowptr_t, int* colidx, int* colidx_t,
-                                                       float* dis, int* flags) {
+                                                       float* dis, int* flags, int* hubitem, int* hubitem_t,
+                                                       int* item_row, int* item_row_t) {
     __shared__ int s_warp[33];
     __shared__ int s_buf[kSortSmemCap];
     const int n = re - rb;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < n; i += nt) { cnt[i] = 0; cnt_t[i] = 0; }
-    if (tid < 3) flags[tid] = 0;
+    if (tid < 5) flags[tid] = 0;
     __syncthreads();
     count_edges(src, dst, E, N, rb, re, normalize, cnt, cnt_t, flags, tid, nt);
     __syncthreads();
@@ -242,6 +284,10 @@ __global__ void __launch_bounds__(1024) k0_build_small(const int64_t* src, const
     sort_rows_cta(rowptr, colidx, 0, n, s_buf);
     __syncthreads();
     sort_rows_cta(rowptr_t, colidx_t, 0, n, s_buf);
+    __syncthreads();
+    list_hubs(rowptr, n, hubitem, item_row, &flags[3], s_warp);
+    __syncthreads();
+    list_hubs(rowptr_t, n, hubitem_t, item_row_t, &flags[4], s_warp);
 }
 
 __global__ void k0_edge_coef(const int* __restrict__ rowptr, const int* __restrict__ colidx,
@@ -256,7 +302,8 @@ __global__ void k0_edge_coef(const int* __restrict__ rowptr, const int* __restri
 }
 
 struct Layout {
-    size_t rowptr, rowptr_t, colidx, colidx_t, dis, cnt, cnt_t, flags, total;
+    size_t rowptr, rowptr_t, colidx, colidx_t, dis, hubitem, hubitem_t, item_row, item_row_t, hub_part, cnt, cnt_t, flags, total;
+    size_t hub_cap;
 };
 Layout make_layout(int64_t E, int32_t n) {
     Layout L;
@@ -267,6 +314,13 @@ Layout make_layout(int64_t E, int32_t n) {
     L.colidx = off;   off += align_up(sizeof(int32_t) * (cap + 1));
     L.colidx_t = off; off += align_up(sizeof(int32_t) * (cap + 1));
     L.dis = off;      off += align_up(sizeof(float) * ((size_t)n + 1));
+    // hub items: sum over hub rows of ceil(deg / kHubChunk) <= 2 * entries / kHubChunk + 1
+    L.hub_cap = 2 * cap / kHubChunk + 2;
+    L.hubitem = off;    off += align_up(sizeof(int32_t) * ((size_t)n + 1));
+    L.hubitem_t = off;  off += align_up(sizeof(int32_t) * ((size_t)n + 1));
+    L.item_row = off;   off += align_up(sizeof(int32_t) * L.hub_cap);
+    L.item_row_t = off; off += align_up(sizeof(int32_t) * L.hub_cap);
+    L.hub_part = off;   off += align_up(sizeof(float) * L.hub_cap * 64);
     L.cnt = off;      off += align_up(sizeof(int32_t) * ((size_t)n + 1));
     L.cnt_t = off;    off += align_up(sizeof(int32_t) * ((size_t)n + 1));
     L.flags = off;    off += align_up(sizeof(int32_t) * 8);
@@ -308,6 +362,13 @@ extern "C" int gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E
     g->colidx = reinterpret_cast<int32_t*>(base + L.colidx);
     g->colidx_t = reinterpret_cast<int32_t*>(base + L.colidx_t);
     g->dis = reinterpret_cast<float*>(base + L.dis);
+    g->hubitem = reinterpret_cast<int32_t*>(base + L.hubitem);
+    g->hubitem_t = reinterpret_cast<int32_t*>(base + L.hubitem_t);
+    g->item_row = reinterpret_cast<int32_t*>(base + L.item_row);
+    g->item_row_t = reinterpret_cast<int32_t*>(base + L.item_row_t);
+    g->hub_part = reinterpret_cast<float*>(base + L.hub_part);
+    g->hub_cap = (int64_t)L.hub_cap;
+    g->nitems = g->nitems_t = -1;
     g->cnt = reinterpret_cast<int32_t*>(base + L.cnt);
     g->cnt_t = reinterpret_cast<int32_t*>(base + L.cnt_t);
     g->flags = reinterpret_cast<int32_t*>(base + L.flags);
@@ -317,7 +378,8 @@ extern "C" int gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E
 
     if (E + n <= kSmallEdgeCap) {
         k0_build_small<<<1, 1024, 0, stream>>>(src, dst, E, N, row_begin, row_end, norm, g->cnt, g->cnt_t,
-                                               g->rowptr, g->rowptr_t, g->colidx, g->colidx_t, g->dis, g->flags);
+                                               g->rowptr, g->rowptr_t, g->colidx, g->colidx_t, g->dis, g->flags,
+                                               g->hubitem, g->hubitem_t, g->item_row, g->item_row_t);
         count_launch();
         if (record(cudaGetLastError()) != GCA_OK) return fail(GCA_ERR_CUDA);
         *out = g;
@@ -342,6 +404,8 @@ extern "C" int gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E
     dim3 grid_s((unsigned)(nblk < 1 ? 1 : (nblk > sms * 8 ? sms * 8 : nblk)), 2);
     k0_sort<<<grid_s, 256, 0, stream>>>(g->rowptr, g->colidx, g->rowptr_t, g->colidx_t, n);
     count_launch();
+    k0_hubs<<<2, 1024, 0, stream>>>(g->rowptr, g->rowptr_t, n, g->hubitem, g->hubitem_t, g->item_row, g->item_row_t, g->flags);
+    count_launch();
     if (record(cudaGetLastError()) != GCA_OK) return fail(GCA_ERR_CUDA);
     *out = g;
     return GCA_OK;
@@ -349,12 +413,14 @@ extern "C" int gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E
 
 extern "C" int gca_graph_validate(gca_graph* g, gca_stream_t stream_, int64_t* nnz, int64_t* nnz_t) {
     if (!g) return GCA_ERR_INVALID_ARG;
-    int32_t h[3] = {0, 0, 0};
+    int32_t h[5] = {0, 0, 0, 0, 0};
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     GCA_CUDA(cudaMemcpyAsync(h, g->flags, sizeof(h), cudaMemcpyDeviceToHost, stream));
     GCA_CUDA(cudaStreamSynchronize(stream));
     if (nnz) *nnz = h[1];
     if (nnz_t) *nnz_t = h[2];
+    g->nitems = h[3];
+    g->nitems_t = h[4];
     return h[0] ? GCA_ERR_INDEX_RANGE : GCA_OK;
 }
 

@@ -76,17 +76,39 @@ __device__ __forceinline__ float4 gather_rows(const float* __restrict__ F, const
     return acc;
 }
 
+// Hub rows: sum of the pre-computed partials of the row's work items, in item order, 8 loads in flight.
+template <int R>
+__device__ __forceinline__ float4 hub_row_sum(const float* __restrict__ hub_part, int first, int nitems, int sub) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < nitems; c0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = (c0 + u < nitems) ? ldg4(hub_part + (size_t)(first + c0 + u) * R + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
+    }
+    return acc;
+}
+
 // One CSR row per lane group (R/4 lanes); every lane of the warp must call this.
+// Rows up to kLongRow neighbours: the group walks them alone.  Up to kHubDeg: the whole warp sweeps the row
+// (fixed shuffle tree).  Longer ("hub") rows: their partial sums were produced by k_hub_partials, one warp per
+// kHubChunk neighbours, and are only added up here.
 template <int R>
 __device__ __forceinline__ float4 warp_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                                 const float* __restrict__ F, int row, bool valid, int lane) {
+                                                 const float* __restrict__ F, int row, bool valid, int lane,
+                                                 const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     const int sub = lane % LPG, grp = lane / LPG;
     int beg = 0, end = 0;
     if (valid) { beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
-    const bool is_long = (end - beg) > kLongRow;
+    const int deg = end - beg;
+    const bool is_hub = deg > kHubDeg;
+    const bool is_long = deg > kLongRow && !is_hub;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!is_long) acc = gather_rows<R>(F, colidx, beg, end, 1, sub);
+    if (is_hub) acc = hub_row_sum<R>(hub_part, __ldg(hubitem + row), (deg + kHubChunk - 1) / kHubChunk, sub);
+    else if (!is_long) acc = gather_rows<R>(F, colidx, beg, end, 1, sub);
     unsigned longmask = __ballot_sync(0xffffffffu, is_long);
     while (longmask) {                                   // warp-uniform
         const int src = __ffs(longmask) - 1;
@@ -100,6 +122,34 @@ __device__ __forceinline__ float4 warp_spmm_rows(const int* __restrict__ rowptr,
         if (grp == g) acc = part;
     }
     return acc;
+}
+
+// Partial sums of the hub work items: one warp per item (kHubChunk consecutive neighbours of a hub row), the
+// lane groups stride over the neighbours, a fixed shuffle tree combines them.  Runs before every hop over the
+// operand that hop gathers; grid-stride over the item count the build left in flags.
+template <int R>
+__global__ void __launch_bounds__(256)
+k_hub_partials(const int* __restrict__ rowptr, const int* __restrict__ colidx, const int* __restrict__ hubitem,
+               const int* __restrict__ item_row, const int* __restrict__ nitems_ptr, const float* __restrict__ F,
+               float* __restrict__ hub_part) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    pdl_wait();
+    pdl_trigger();
+    const int nitems = *nitems_ptr;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPG, grp = lane / LPG;
+    const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wtotal = gridDim.x * (blockDim.x >> 5);
+    for (int item = wglobal; item < nitems; item += wtotal) {
+        const int row = __ldg(item_row + item);
+        const int chunk = item - __ldg(hubitem + row);
+        const int rbeg = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
+        const int b = rbeg + chunk * kHubChunk;
+        const int e = min(rend, b + kHubChunk);
+        float4 part = gather_rows<R>(F, colidx, b + grp, e, GPW, sub);
+#pragma unroll
+        for (int off = LPG; off < 32; off <<= 1) part = f4_add(part, f4_shfl_xor(part, off));
+        if (grp == 0) *reinterpret_cast<float4*>(hub_part + (size_t)item * R + sub * 4) = part;
+    }
 }
 
 __device__ __forceinline__ float act_apply(float h, int act) {
@@ -211,7 +261,8 @@ __global__ void __launch_bounds__(256)
 k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
       const float* __restrict__ F, const float* __restrict__ bias, int act,
       const float* __restrict__ Zp_saved, const float* __restrict__ H1_saved,
-      float* __restrict__ out, float* __restrict__ H1_out, float* __restrict__ part_bd, int* header, int n) {
+      float* __restrict__ out, float* __restrict__ H1_out, float* __restrict__ part_bd, int* header, int n,
+      const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPG, grp = lane / LPG;
@@ -224,7 +275,7 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
     for (int rowbase = wglobal * GPW; rowbase < n; rowbase += wtotal * GPW) {
         const int row = rowbase + grp;
         const bool valid = row < n;
-        const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+        const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane, hubitem, hub_part);
         if (!valid) continue;
         const float di = __ldg(dis + row);
         const size_t o = (size_t)row * R + sub * 4;
@@ -274,7 +325,8 @@ k_hop_expand(const int* __restrict__ rowptr, const int* __restrict__ colidx, con
              const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
              const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
              int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
-             int n, int d) {
+             int n, int d,
+    const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     extern __shared__ __align__(16) float smem[];
     float* WT = smem;                 // [R][d]
@@ -298,7 +350,7 @@ k_hop_expand(const int* __restrict__ rowptr, const int* __restrict__ colidx, con
         for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
             const int row = trow + rr + grp;
             const bool valid = row < n;
-            const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+            const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane, hubitem, hub_part);
             float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 h = f4_scale(acc, __ldg(dis + row));
@@ -625,7 +677,8 @@ k_hop_expand_mma(const int* __restrict__ rowptr, const int* __restrict__ colidx,
                  const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
                  const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
                  int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
-                 int n, int d) {
+                 int n, int d,
+    const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     constexpr int RS = R + 4;                       // padded row stride of the H tile
     constexpr int KS = R / 8;                       // k-steps
@@ -659,7 +712,7 @@ k_hop_expand_mma(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
             const int row = trow + rr + grp;
             const bool valid = row < n;
-            const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+            const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane, hubitem, hub_part);
             float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 h = f4_scale(acc, __ldg(dis + row));
@@ -761,7 +814,8 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
                 const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
                 int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
-                int n, int d) {
+                int n, int d,
+    const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     constexpr int RS = R + 4;
     constexpr int KS = R / 8;
@@ -799,7 +853,7 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
                 const int row = trow + rr + grp;
                 const bool valid = row < n;
-                const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane);
+                const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane, hubitem, hub_part);
                 float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
                     h = f4_scale(acc, __ldg(dis + row));
@@ -1221,27 +1275,54 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
     return GCA_OK;
 }
 
+// CSR view of one direction of a graph handle (+ its hub work items).
+struct Csr {
+    const int* rowptr; const int* colidx; const float* dis;
+    const int* hubitem; const int* item_row; const int* nitems_ptr; float* hub_part; int nitems_host;
+};
+inline Csr csr_of(const gca_graph* g, bool transpose) {
+    return transpose ? Csr{g->rowptr_t, g->colidx_t, g->dis, g->hubitem_t, g->item_row_t, g->flags + 4, g->hub_part, g->nitems_t}
+                     : Csr{g->rowptr, g->colidx, g->dis, g->hubitem, g->item_row, g->flags + 3, g->hub_part, g->nitems};
+}
+// Partial sums of the hub rows over operand F (skipped when the validated build found no hub row).
+template <int R>
+int launch_hub_partials(const Csr& c, const float* F, cudaStream_t st) {
+    if (c.nitems_host == 0) return GCA_OK;
+    int grid = c.nitems_host > 0 ? (c.nitems_host + 7) / 8 : 2 * num_sms();
+    if (grid > 8 * num_sms()) grid = 8 * num_sms();
+    {
+        ProfScope ps("hub_partials", st);
+        GCA_CUDA(launch_pdl(k_hub_partials<R>, dim3(grid), dim3(256), 0, st, c.rowptr, c.colidx, c.hubitem, c.item_row, c.nitems_ptr, F, c.hub_part));
+    }
+    GCA_LAUNCH_OK();
+    return GCA_OK;
+}
+
 template <int R, bool BWD>
-int launch_hop(const int* rowptr, const int* colidx, const float* dis, const float* F, const float* bias, int act,
+int launch_hop(const Csr& c, const float* F, const float* bias, int act,
                const float* Zp, const float* H1s, float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st) {
     constexpr int GPW = 32 / (R / 4);
+    GCA_TRY(launch_hub_partials<R>(c, F, st));
+    const int* rowptr = c.rowptr; const int* colidx = c.colidx; const float* dis = c.dis;
     int grid = (n + 8 * GPW - 1) / (8 * GPW);
     const int cap = BWD ? (kMaxPartsBd < 8 * num_sms() ? kMaxPartsBd : 8 * num_sms()) : 8 * num_sms();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     {
         ProfScope ps(BWD ? "hop_bwd" : "hop_fwd", st);
-        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n));
+        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, c.hubitem, c.hub_part));
     }
     GCA_LAUNCH_OK();
     return GCA_OK;
 }
 
 template <int R, bool W_IS_DR>
-int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, const float* F, const float* W,
+int launch_hop_expand(const Csr& c, const float* F, const float* W,
                       const float* bias, const float* resid, int64_t ldr, const float* scalar, int alpha_is_scalar,
                       int use_resid, float* Hout, float* Out, int64_t ldo, int n, int d, cudaStream_t st) {
     if (n == 0) return GCA_OK;
+    GCA_TRY(launch_hub_partials<R>(c, F, st));
+    const int* rowptr = c.rowptr; const int* colidx = c.colidx; const float* dis = c.dis;
     if constexpr (R == 16 || R == 32) {
         if (tc_enabled()) {
             static const int use_ws = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && e[0] == 'm') ? 0 : 1; }();
@@ -1253,7 +1334,7 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
                 {
                     ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
                     GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR>, dim3(grid_w), dim3(512), smem_ws, st, rowptr, colidx, dis, F, W, bias,
-                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d));
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part));
                 }
                 GCA_LAUNCH_OK();
                 return GCA_OK;
@@ -1266,7 +1347,7 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
                 {
                     ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
                     k_hop_expand_mma<R, W_IS_DR><<<grid_m, 256, smem_m, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
-                                                                              alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+                                                                              alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part);
                 }
                 GCA_LAUNCH_OK();
                 return GCA_OK;
@@ -1281,7 +1362,7 @@ int launch_hop_expand(const int* rowptr, const int* colidx, const float* dis, co
     {
         ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
         k_hop_expand<R, W_IS_DR><<<grid, 256, smem, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
-                                                           alpha_is_scalar, use_resid, Hout, Out, ldo, n, d);
+                                                           alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part);
     }
     GCA_LAUNCH_OK();
     return GCA_OK;
@@ -1365,7 +1446,7 @@ extern "C" int gca_fwd_hop1(const gca_graph* g, const float* Pp_full, const floa
     if (act == GCA_ACT_SILU && !H1_local) return GCA_ERR_INVALID_ARG;
     const int n = g->row_end - g->row_begin;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GCA_DISPATCH_R(r, (launch_hop<R_, false>(g->rowptr, g->colidx, g->dis, Pp_full, bd, act, nullptr, nullptr,
+    GCA_DISPATCH_R(r, (launch_hop<R_, false>(csr_of(g, false), Pp_full, bd, act, nullptr, nullptr,
                                              Zp_local, H1_local, nullptr, nullptr, n, st)));
 }
 
@@ -1377,7 +1458,7 @@ extern "C" int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full, const f
     if (!shape_ok(d, r) || (ldy % 4) != 0 || (skip && (ldx % 4) != 0)) return GCA_ERR_UNSUPPORTED;
     const int n = g->row_end - g->row_begin;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GCA_DISPATCH_R(r, (launch_hop_expand<R_, true>(g->rowptr, g->colidx, g->dis, Zp_full, Wu, bu, X, ldx, scalar, 1,
+    GCA_DISPATCH_R(r, (launch_hop_expand<R_, true>(csr_of(g, false), Zp_full, Wu, bu, X, ldx, scalar, 1,
                                                    skip ? 1 : 0, H2_local, Y, ldy, n, d, st)));
 }
 
@@ -1429,7 +1510,7 @@ template <int R>
 int bwd_hop1_down_impl(const gca_graph* g, const float* gH1p_full, const float* X, int64_t ldx, const float* gY,
                        int64_t ldg, const float* Wd, const float* scalar, int skip, float* gP, float* gX, int64_t ldgx,
                        const Scratch& S, int n, int d, cudaStream_t st) {
-    GCA_TRY((launch_hop_expand<R, false>(g->rowptr_t, g->colidx_t, g->dis, gH1p_full, Wd, nullptr, gY, ldg, scalar, 0,
+    GCA_TRY((launch_hop_expand<R, false>(csr_of(g, true), gH1p_full, Wd, nullptr, gY, ldg, scalar, 0,
                                          skip ? 1 : 0, gP, gX, ldgx, n, d, st)));
     const bool want_dot = skip && scalar;
     return launch_wgrad<R>(X, ldx, gP, want_dot ? gY : nullptr, ldg, S.gd, nullptr, want_dot ? S.dot : nullptr,
@@ -1459,7 +1540,7 @@ extern "C" int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full, const fl
     const int n = g->row_end - g->row_begin;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Scratch S = scratch_ptrs(scratch, 4, r);      // header / bd offsets do not depend on d
-    GCA_DISPATCH_R(r, (launch_hop<R_, true>(g->rowptr_t, g->colidx_t, g->dis, gH2p_full, nullptr, act, Zp_local,
+    GCA_DISPATCH_R(r, (launch_hop<R_, true>(csr_of(g, true), gH2p_full, nullptr, act, Zp_local,
                                             H1_local, gH1p_local, nullptr, S.bd, S.header, n, st)));
 }
 

@@ -143,6 +143,20 @@ def test_config3_arxiv_power_law_quarter_scale():
     _oracle_parity(ei, n, 256, 16, seed=4, tag="arxiv power law")
 
 
+def test_hub_rows_take_the_work_item_path():
+    """A star (hub degree 6000 > kHubDeg = 512, cut into 512-neighbour work items) plus a random graph, directed
+    extra edges into a second hub: exercises k_hub_partials and the ordered partial sums in all four hops."""
+    n = 6001
+    leaves = torch.arange(1, n, dtype=torch.int64)
+    hub = torch.zeros(n - 1, dtype=torch.int64)
+    rnd = symmetric_random_graph(n, 20000, seed=17)
+    into7 = torch.randint(1, n, (1500,), generator=torch.Generator().manual_seed(3))       # directed: only in-edges
+    ei = torch.cat([torch.stack([hub, leaves]), torch.stack([leaves, hub]), rnd,
+                    torch.stack([into7, torch.full_like(into7, 7)])], dim=1)
+    _oracle_parity(ei, n, 64, 16, seed=21, tag="hub star")
+    _oracle_parity(ei, n, 64, 32, seed=22, tag="hub star r=32", normalize=False)
+
+
 def test_config4_products_shaped_scaled():
     """configs[4] shape (hidden 256, rank 32) at 1/64 scale; the full size is covered by properties."""
     ei, n = make_graph("products", seed=0, scale=1 / 64)
