@@ -120,13 +120,13 @@ class _GConvAdapterFunction(torch.autograd.Function):
         h1_ptr = base + 2 * rw if ctx.silu else None
         need_x = ctx.needs_input_grad[0]
         g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
-        # parameter gradients in one allocation: [gWd | gWu | gbu | gbd | gs]
-        flat = torch.empty(2 * d * r + d + r + 1, dtype=torch.float32, device=dev)
-        g_wd = flat[0:d * r].view(r, d)
-        g_wu = flat[d * r:2 * d * r].view(d, r)
-        g_bu = flat[2 * d * r:2 * d * r + d]
-        g_bd = flat[2 * d * r + d:2 * d * r + d + r]
-        g_s = flat[2 * d * r + d + r:] if scalar is not None else None
+        # one fresh (non-view) tensor per parameter gradient, so autograd's AccumulateGrad can take ownership
+        # of it instead of cloning
+        g_wd = torch.empty((r, d), dtype=torch.float32, device=dev)
+        g_wu = torch.empty((d, r), dtype=torch.float32, device=dev)
+        g_bu = torch.empty((d,), dtype=torch.float32, device=dev)
+        g_bd = torch.empty((r,), dtype=torch.float32, device=dev)
+        g_s = torch.empty((1,), dtype=torch.float32, device=dev) if scalar is not None else None
         ws = torch.empty(_sizes(lib, n, d, r)[1], dtype=torch.uint8, device=dev)
         _cabi.check(lib.gca_backward(ctx.graph.handle, g_y.data_ptr(), g_y.stride(0), x.data_ptr(), x.stride(0),
                                      zp_ptr, h1_ptr, h2_ptr, w_down.data_ptr(), w_up.data_ptr(),
