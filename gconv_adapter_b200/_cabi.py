@@ -46,6 +46,8 @@ SIGNATURES = {
     "gca_fwd_hop2_up": (C.c_int, [_f, _f, _f, _i64, _f, _f, _f, C.c_int, _f, _f, _i64, _i32, _i32, _f]),
     "gca_bwd_scratch_bytes": (_sz, [_i32, _i32]),
     "gca_bwd_up": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f]),
+    "gca_bwd_up_project": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _i32, _i32, _f]),
+    "gca_bwd_up_wgrad": (C.c_int, [_f, _f, _i64, _f, _f, _i32, _i32, _f]),
     "gca_bwd_hop2": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _i32, _f]),
     "gca_bwd_hop1_down": (C.c_int, [_f, _f, _f, _i64, _f, _i64, _f, _f, C.c_int, _f, _f, _i64, _f, _i32, _i32, _f]),
     "gca_bwd_finalize": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _f, _f, _f, _i32, _i32, _f]),

@@ -1531,6 +1531,28 @@ extern "C" int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, cons
     GCA_DISPATCH_R(r, (bwd_up_impl<R_>(g, gY, ldg, H2_local, Wu, scalar, gH2p_local, S, n, d, st)));
 }
 
+extern "C" int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t ldg, const float* Wu, const float* scalar,
+                                  float* gH2p_local, void* scratch, int32_t d, int32_t r, gca_stream_t stream) {
+    if (!g || !gY || !Wu || !gH2p_local || !scratch || ldg < d) return GCA_ERR_INVALID_ARG;
+    if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Scratch S = scratch_ptrs(scratch, d, r);
+    GCA_CUDA(cudaMemsetAsync(S.header, 0, 256, st));
+    GCA_DISPATCH_R(r, (launch_project<R_, false>(gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, st)));
+}
+
+extern "C" int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, void* scratch,
+                                int32_t d, int32_t r, gca_stream_t stream) {
+    if (!g || !gY || !H2_local || !scratch || ldg < d) return GCA_ERR_INVALID_ARG;
+    if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
+    const int n = g->row_end - g->row_begin;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Scratch S = scratch_ptrs(scratch, d, r);
+    GCA_DISPATCH_R(r, (launch_wgrad<R_>(gY, ldg, H2_local, nullptr, 0, S.gu, S.col, nullptr, S.header, 0, n, d, st)));
+}
+
 extern "C" int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full, const float* Zp_local, const float* H1_local,
                             int act, float* gH1p_local, void* scratch, int32_t r, gca_stream_t stream) {
     if (!g || !gH2p_full || !gH1p_local || !scratch) return GCA_ERR_INVALID_ARG;

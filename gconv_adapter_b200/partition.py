@@ -83,6 +83,16 @@ class CudaPhases:
                                         _ptr(scalar), gh2_local.data_ptr(), scratch.data_ptr(), d, r,
                                         self._stream(gy)), "gca_bwd_up")
 
+    def bwd_up_project(self, g, gy, wu, scalar, gh2_local, scratch):
+        d, r = wu.shape
+        _cabi.check(self.lib.gca_bwd_up_project(g.handle, gy.data_ptr(), gy.stride(0), wu.data_ptr(), _ptr(scalar),
+                                                gh2_local.data_ptr(), scratch.data_ptr(), d, r, self._stream(gy)),
+                    "gca_bwd_up_project")
+
+    def bwd_up_wgrad(self, g, gy, h2_local, scratch, d, r):
+        _cabi.check(self.lib.gca_bwd_up_wgrad(g.handle, gy.data_ptr(), gy.stride(0), h2_local.data_ptr(),
+                                              scratch.data_ptr(), d, r, self._stream(gy)), "gca_bwd_up_wgrad")
+
     def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch):
         r = gh2_full.shape[1]
         _cabi.check(self.lib.gca_bwd_hop2(g.handle, gh2_full.data_ptr(), z_local.data_ptr(), _ptr(h1_local), act,
@@ -103,11 +113,11 @@ class CudaPhases:
                                               _ptr(g_s), d, r, self._stream(wu)), "gca_bwd_finalize")
 
 
-def _all_gather_rows(full: torch.Tensor, lo: int, s: int, group) -> None:
+def _all_gather_rows(full: torch.Tensor, lo: int, s: int, group, async_op: bool = False):
     """In-place all-gather: every rank contributes rows [rank*S, (rank+1)*S) of ``full``."""
     if dist.get_world_size(group) == 1:
-        return
-    dist.all_gather_into_tensor(full, full[lo:lo + s], group=group)
+        return None
+    return dist.all_gather_into_tensor(full, full[lo:lo + s], group=group, async_op=async_op)
 
 
 class _PartitionedFunction(torch.autograd.Function):
@@ -169,10 +179,20 @@ class _PartitionedFunction(torch.autograd.Function):
         g_bu = flat[2 * d * r:2 * d * r + d]
         g_bd = flat[2 * d * r + d:2 * d * r + d + r]
         g_s = flat[2 * d * r + d + r:]
+        # gH2' first, then its all-gather runs (on NCCL's stream) while the weight-gradient half of the same
+        # phase - which does not need remote rows - keeps this GPU busy
+        split = hasattr(backend, "bwd_up_project")
         if n > 0:
             scratch = backend.bwd_scratch(d, r, dev)
-            backend.bwd_up(graph, g_y, h2, w_up, scalar, gh2_full[lo:lo + n], scratch)
-        _all_gather_rows(gh2_full, lo, s, group)
+            if split:
+                backend.bwd_up_project(graph, g_y, w_up, scalar, gh2_full[lo:lo + n], scratch)
+            else:
+                backend.bwd_up(graph, g_y, h2, w_up, scalar, gh2_full[lo:lo + n], scratch)
+        work = _all_gather_rows(gh2_full, lo, s, group, async_op=split)
+        if n > 0 and split:
+            backend.bwd_up_wgrad(graph, g_y, h2, scratch, d, r)
+        if work is not None:
+            work.wait()
         if n > 0:
             backend.bwd_hop2(graph, gh2_full, z_full[lo:lo + n], h1, ctx.act, gh1_full[lo:lo + n], scratch)
         _all_gather_rows(gh1_full, lo, s, group)

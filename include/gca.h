@@ -122,6 +122,13 @@ size_t gca_bwd_scratch_bytes(int32_t d, int32_t r);
 int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local,
                const float* Wu, const float* scalar, float* gH2p_local /*[n,r]*/,
                void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+/* The two halves of gca_bwd_up as separate calls, so that a multi-GPU caller can start the all-gather of gH2'
+ * between them (the weight-gradient half does not depend on it): _project clears the scratch header and writes
+ * gH2', _wgrad accumulates the gWu / gbu partials. */
+int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t ldg, const float* Wu, const float* scalar,
+                       float* gH2p_local, void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, void* scratch,
+                     int32_t d, int32_t r, gca_stream_t stream);
 /* gH1'[j] = dis[j] * act'(.) * dis[j] * sum_{i in out(j)} gH2'[i] ; partial sums for gbd */
 int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full /*[N,r]*/, const float* Zp_local,
                  const float* H1_local /*NULL unless silu*/, int act, float* gH1p_local /*[n,r]*/,

@@ -58,6 +58,14 @@ class CpuPhases:
         scratch["gu"] = gy.t() @ h2_local[:n]          # [d, r], unscaled
         scratch["col"] = gy.sum(0)
 
+    def bwd_up_project(self, g, gy, wu, scalar, gh2_local, scratch):
+        s = scalar if scalar is not None else torch.ones(1)
+        gh2_local.copy_(g.dis[:, None] * s * (gy @ wu))
+
+    def bwd_up_wgrad(self, g, gy, h2_local, scratch, d, r):
+        scratch["gu"] = gy.t() @ h2_local[:gy.shape[0]]
+        scratch["col"] = gy.sum(0)
+
     def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch):
         gz = g.dis[:, None] * g.agg(gh2_full, transpose=True)
         n = gz.shape[0]
