@@ -1308,27 +1308,29 @@ k_bwd_up_fused(const float* __restrict__ gY, int64_t ldg, const float* __restric
 // split the partial rows (warp w sums rows w, w+8, ... with 8 loads in flight), their 8 sums are added in warp
 // order through shared memory, and warp 0 writes the result.  The last CTA to finish adds up the gscalar pieces.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 sum_rows_strided(const float* __restrict__ base, int np, size_t pitch, int first, bool ok) {
+constexpr int kFinWarps = 16;
+__device__ __forceinline__ float4 sum_rows_strided(const float* __restrict__ base, int np, size_t pitch, int first, int stride,
+                                                   bool ok) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!ok) return acc;
-    for (int p = first; p < np; p += 64) {          // 8 predicated loads in flight, no serial tail
+    for (int p = first; p < np; p += 8 * stride) {   // 8 predicated loads in flight, no serial tail
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            v[u] = (p + 8 * u < np) ? ldg4(base + (size_t)(p + 8 * u) * pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u] = (p + stride * u < np) ? ldg4(base + (size_t)(p + stride * u) * pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
     }
     return acc;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinWarps * 32)
 k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, const float* __restrict__ partGd,
            const float* __restrict__ partDot, const float* __restrict__ partBd, float* gsp, int* header,
            const float* __restrict__ Wu, const float* __restrict__ bu, const float* __restrict__ scalar, int skip,
            float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar, int d, int r) {
-    __shared__ float4 s_part[8][32];
-    __shared__ float s_red[256];
+    __shared__ float4 s_part[kFinWarps][32];
+    __shared__ float s_red[kFinWarps * 32];
     __shared__ int s_last;
     pdl_wait();
     const int pu = header[0], pd = header[1], pb = header[2];
@@ -1348,16 +1350,24 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
         const int np = kind == 0 ? pu : kind == 1 ? pd : kind == 2 ? pu : pb;
         const int nq = kind <= 1 ? rd4 : kind == 2 ? d4 : r4;
         const size_t pitch = kind <= 1 ? (size_t)r * d : kind == 2 ? (size_t)d : (size_t)r;
-        const int q = blk * 32 + lane;
-        const bool ok = q < nq && !(kind == 1 && !gWd) && !(kind == 3 && !gbd);
-        const float4 mine = sum_rows_strided(part + (size_t)q * 4, np, pitch, warp, ok);
+        // the bias partials are only r floats wide but there are many of them (one per CTA of the transpose hop):
+        // the 32 / r4 lane groups of a warp take different partial rows and are combined by a fixed butterfly
+        const bool narrow = kind == 3 && r4 < 32 && (32 % r4) == 0;
+        const int groups = narrow ? 32 / r4 : 1;
+        const int q = narrow ? lane % r4 : blk * 32 + lane;
+        const int first = narrow ? warp * groups + lane / r4 : warp;
+        const bool live = q < nq && !(kind == 1 && !gWd) && !(kind == 3 && !gbd);
+        float4 mine = sum_rows_strided(part + (size_t)q * 4, np, pitch, first, kFinWarps * groups, live);
+        if (narrow)
+            for (int off = r4; off < 32; off <<= 1) mine = f4_add(mine, f4_shfl_xor(mine, off));
+        const bool ok = live && (!narrow || lane < r4);
         __syncthreads();
         s_part[warp][lane] = mine;
         __syncthreads();
         if (warp == 0 && ok) {
             float4 t = s_part[0][lane];
 #pragma unroll
-            for (int w = 1; w < 8; ++w) t = f4_add(t, s_part[w][lane]);
+            for (int w = 1; w < kFinWarps; ++w) t = f4_add(t, s_part[w][lane]);
             if (kind == 0) {
                 const int c = (q * 4) / d, k = q * 4 - c * d;
                 const float g4[4] = {t.x, t.y, t.z, t.w};
@@ -1378,26 +1388,33 @@ k_finalize(const float* __restrict__ partGu, const float* __restrict__ partCol, 
         }
     }
     if (!gscalar) return;
+    auto block_sum = [&](float v) {                    // fixed-order tree over the CTA
+        __syncthreads();
+        s_red[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = kFinWarps * 16; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+            __syncthreads();
+        }
+        return s_red[0];
+    };
     if (skip && blockIdx.x == 0)
         for (int p = threadIdx.x; p < pd; p += blockDim.x) gs += partDot[p];
-    s_red[threadIdx.x] = gs;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-        __syncthreads();
-    }
+    const float mine_gs = block_sum(gs);
     if (threadIdx.x == 0) {
-        gsp[blockIdx.x] = s_red[0];
+        gsp[blockIdx.x] = mine_gs;
         __threadfence();
         s_last = (atomicAdd(&header[3], 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {                                      // gridDim.x <= kMaxFin <= blockDim.x
         __threadfence();
-        float t = 0.f;
-        for (int b = 0; b < (int)gridDim.x; ++b) t += reinterpret_cast<volatile float*>(gsp)[b];
-        *gscalar = t;
-        header[3] = 0;
+        const float v = threadIdx.x < gridDim.x ? reinterpret_cast<volatile float*>(gsp)[threadIdx.x] : 0.f;
+        const float total = block_sum(v);
+        if (threadIdx.x == 0) {
+            *gscalar = total;
+            header[3] = 0;
+        }
     }
 }
 
@@ -1794,7 +1811,7 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
     if (grid > kMaxFin) grid = kMaxFin;
     {
         ProfScope ps("finalize", static_cast<cudaStream_t>(stream));
-        GCA_CUDA(launch_pdl(k_finalize, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), S.gu, S.col, S.gd, S.dot, S.bd,
+        GCA_CUDA(launch_pdl(k_finalize, dim3(grid), dim3(kFinWarps * 32), 0, static_cast<cudaStream_t>(stream), S.gu, S.col, S.gd, S.dot, S.bd,
                             S.gsp, S.header, Wu, bu, scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r));
     }
     GCA_LAUNCH_OK();
