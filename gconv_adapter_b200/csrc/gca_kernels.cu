@@ -843,29 +843,89 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 
     if (warp < 8) {
         // ===================== gather warps =====================
+        // A warp owns GPW rows of every pass (PASSES passes of 8 * GPW rows per tile).  The three dependent
+        // round trips of a row (rowptr -> colidx -> neighbour rows) are software-pipelined over the warp's
+        // sequence of passes: step s issues the rowptr/dis loads of step s+2, the (first kPre) colidx loads of
+        // step s+1 and the neighbour-row loads of step s back to back, so a step costs ONE memory latency.
         const int sub = lane % LPG, grp = lane / LPG;
-        for (int k = 0; k < my_tiles; ++k) {
-            const int b = k & 1;
-            const int trow = (blockIdx.x + k * gridDim.x) * kTileRows;
-            if (k >= 2) named_sync(kEmpty + b, 512);           // expand warps are done with this buffer
+        constexpr int PASSES = kTileRows / (8 * GPW);
+        constexpr int kPre = 16;                                // neighbours covered by the pipelined fast path
+        const int nsteps = my_tiles * PASSES;
+        auto row_of = [&](int s_) {
+            const int k_ = s_ / PASSES, ps = s_ - k_ * PASSES;
+            return (blockIdx.x + k_ * (int)gridDim.x) * kTileRows + ps * 8 * GPW + warp * GPW + grp;
+        };
+        struct Meta { int beg, end; float dis; };
+        auto meta_load = [&](int s_) {
+            Meta m{0, 0, 0.f};
+            if (s_ < nsteps) {
+                const int row = row_of(s_);
+                if (row < n) { m.beg = __ldg(rowptr + row); m.end = __ldg(rowptr + row + 1); m.dis = __ldg(dis + row); }
+            }
+            return m;
+        };
+        auto idx_load = [&](const Meta& m, int (&j)[kPre]) {
+            const bool fast = m.end - m.beg <= kLongRow;        // long / hub rows take the collective paths below
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) j[u] = (fast && m.beg + u < m.end) ? __ldg(colidx + m.beg + u) : -1;
+        };
+        Meta m0 = meta_load(0), m1 = meta_load(1);
+        int j0[kPre], j1[kPre];
+        idx_load(m0, j0);
+        for (int s_ = 0; s_ < nsteps; ++s_) {
+            const int k = s_ / PASSES, ps = s_ - k * PASSES, b = k & 1;
+            const Meta m2 = meta_load(s_ + 2);
+            idx_load(m1, j1);
+            float4 v[kPre];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u)
+                v[u] = (j0[u] >= 0) ? ldg4(F + (size_t)j0[u] * R + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) acc = f4_add(acc, v[u]);
+            const int row = row_of(s_);
+            const bool valid = row < n;
+            const int deg = m0.end - m0.beg;
+            const bool is_hub = deg > kHubDeg;
+            const bool is_long = deg > kLongRow && !is_hub;
+            if (is_hub) {
+                acc = hub_row_sum<R>(hub_part, __ldg(hubitem + row), (deg + kHubChunk - 1) / kHubChunk, sub);
+            } else if (!is_long && deg > kPre) {                 // the rest of a medium row, same order as before
+                const float4 rest = gather_rows<R>(F, colidx, m0.beg + kPre, m0.end, 1, sub);
+                acc = f4_add(acc, rest);
+            }
+            unsigned longmask = __ballot_sync(0xffffffffu, is_long);
+            while (longmask) {                                   // warp-uniform
+                const int src = __ffs(longmask) - 1;
+                const int g_ = src / LPG;
+                const unsigned gm = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << (g_ * LPG));
+                longmask &= ~gm;
+                const int lb = __shfl_sync(0xffffffffu, m0.beg, src), le = __shfl_sync(0xffffffffu, m0.end, src);
+                float4 part = gather_rows<R>(F, colidx, lb + grp, le, GPW, sub);
+#pragma unroll
+                for (int off = LPG; off < 32; off <<= 1) part = f4_add(part, f4_shfl_xor(part, off));
+                if (grp == g_) acc = part;
+            }
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                h = f4_scale(acc, m0.dis);
+                *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
+            }
+            uint4 hi, lo;
+            split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+            if (ps == 0 && k >= 2) named_sync(kEmpty + b, 512);  // expand warps are done with this buffer
             uint32_t* Hh = Hbuf + (size_t)b * 2 * kTileRows * RS;
             uint32_t* Hl = Hh + kTileRows * RS;
-            for (int rr = warp * GPW; rr < kTileRows; rr += 8 * GPW) {
-                const int row = trow + rr + grp;
-                const bool valid = row < n;
-                const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane, hubitem, hub_part);
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    h = f4_scale(acc, __ldg(dis + row));
-                    *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
-                }
-                uint4 hi, lo;
-                split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
-                *reinterpret_cast<uint4*>(&Hh[(rr + grp) * RS + sub * 4]) = hi;
-                *reinterpret_cast<uint4*>(&Hl[(rr + grp) * RS + sub * 4]) = lo;
+            const int hr = ps * 8 * GPW + warp * GPW + grp;
+            *reinterpret_cast<uint4*>(&Hh[hr * RS + sub * 4]) = hi;
+            *reinterpret_cast<uint4*>(&Hl[hr * RS + sub * 4]) = lo;
+            if (ps == PASSES - 1) {
+                __threadfence_block();
+                named_arrive(kFull + b, 512);
             }
-            __threadfence_block();
-            named_arrive(kFull + b, 512);
+            m0 = m1; m1 = m2;
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
         }
     } else {
         // ===================== expand warps =====================
