@@ -808,7 +808,52 @@ k_hop_expand_mma(const int* __restrict__ rowptr, const int* __restrict__ colidx,
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int R, bool W_IS_DR>
+// mbarrier + bulk-copy (TMA) helpers for the residual stream of K3-ws
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+#ifdef GCA_WS_DEBUG
+// cycles summed over CTAs (lane 0 of expand warp 8 / gather warp 0): [0] expand wait-FULL, [1] MMA issue, [2] wait residual,
+// [3] epilogue + stores, [4] expand total, [5] gather wait-EMPTY, [6] gather total
+__device__ unsigned long long g_ws_dbg[16];
+#define WS_T(var) const long long var = clock64()
+#define WS_ADD(slot, expr) ws_acc[slot] += (expr)
+#else
+#define WS_T(var)
+#define WS_ADD(slot, expr)
+#endif
+
+// XT = true: the residual tile [64, d] of the next tile is brought into shared memory by bulk copies (one per
+// row, issued by the gather warps as soon as the expand warps released the buffer, completion on an mbarrier)
+// instead of register prefetches by the expand warps.  The register version is bounded by the way the loads
+// are tracked (profiles/README.md, "single scoreboard"): the first use of ANY prefetched residual waits for ALL
+// outstanding ones, so the tensor-core phase and the memory wait of a warp never overlap.
+template <int R, bool W_IS_DR, bool XT>
 __global__ void __launch_bounds__(512, 1)
 k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
                 const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
@@ -820,12 +865,23 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
     constexpr int RS = R + 4;
     constexpr int KS = R / 8;
     constexpr int MTS = kTileRows / 16;             // m-tiles per tile (4)
-    constexpr int kFull = 1, kEmpty = 3;            // named barrier ids: kFull + b, kEmpty + b
+    constexpr int kFull = 1, kEmpty = 3, kPhase = 5; // named barrier ids: kFull + b, kEmpty + b
     extern __shared__ __align__(16) uint32_t smem_u[];
     const int WS = d + 1;
     uint32_t* Wh = smem_u;                          // [R][WS]
     uint32_t* Wl = Wh + (size_t)R * WS;
     uint32_t* Hbuf = Wl + (size_t)R * WS;           // [2 buffers][hi, lo][64][RS]
+    // XT: residual stages [2][64][XS] floats (row stride d + 16 floats: 16-byte aligned, and for d % 32 == 0 the
+    // rows g / g+1 of a quarter warp fall into different bank halves) + two mbarriers
+    const int XS = d + 16;
+    float* Xs = reinterpret_cast<float*>(Hbuf + (size_t)4 * kTileRows * RS + (((size_t)2 * R * WS) & 1));   // keep 16-byte alignment
+    Xs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Xs) + 15) & ~(uintptr_t)15);
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(Xs + (size_t)2 * kTileRows * XS);
+    if (XT && threadIdx.x == 0) {
+        mbar_init(smem_addr(&xbar[0]), 8);
+        mbar_init(smem_addr(&xbar[1]), 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
         int k, c;
         if (W_IS_DR) { k = idx / R; c = idx - k * R; } else { c = idx / d; k = idx - c * d; }
@@ -840,6 +896,10 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ntiles = (n + kTileRows - 1) / kTileRows;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#ifdef GCA_WS_DEBUG
+    long long ws_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long ws_t0 = clock64();
+#endif
 
     if (warp < 8) {
         // ===================== gather warps =====================
@@ -913,7 +973,19 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             }
             uint4 hi, lo;
             split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+            WS_T(tg0);
             if (ps == 0 && k >= 2) named_sync(kEmpty + b, 512);  // expand warps are done with this buffer
+            WS_T(tg1); WS_ADD(5, tg1 - tg0);
+            if (XT && ps == 0 && lane == 0) {                    // this warp's 8 residual rows of tile k
+                const int xr0 = (blockIdx.x + k * (int)gridDim.x) * kTileRows + warp * 8;
+                const int nrows = max(0, min(8, n - xr0));
+                const uint32_t bar = smem_addr(&xbar[b]);
+                mbar_arrive_expect_tx(bar, (uint32_t)nrows * (uint32_t)d * 4u);
+                const uint64_t pol = policy_evict_first();
+                for (int i = 0; i < nrows; ++i)
+                    bulk_load_row(smem_addr(Xs + ((size_t)b * kTileRows + warp * 8 + i) * XS), resid + (size_t)(xr0 + i) * ldr,
+                                  (uint32_t)d * 4u, bar, pol);
+            }
             uint32_t* Hh = Hbuf + (size_t)b * 2 * kTileRows * RS;
             uint32_t* Hl = Hh + kTileRows * RS;
             const int hr = ps * 8 * GPW + warp * GPW + grp;
@@ -927,6 +999,9 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
         }
+#ifdef GCA_WS_DEBUG
+        if (warp == 0 && lane == 0) { atomicAdd(&g_ws_dbg[5], ws_acc[5]); atomicAdd(&g_ws_dbg[6], clock64() - ws_t0); }
+#endif
     } else {
         // ===================== expand warps =====================
         const int g = lane >> 2, t = lane & 3;
@@ -944,6 +1019,90 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         const bool o0 = blk_ok && oc < d, o1 = blk_ok && oc1 < d;
         float4 b4a = make_float4(0.f, 0.f, 0.f, 0.f), b4b = b4a;
         if (bias) { if (o0) b4a = ldg4(bias + oc); if (o1) b4b = ldg4(bias + oc1); }
+        auto fin = [&](float a0, float a1, float a2, float a3, const float4& b4, const float4& xv) {
+            float4 y = make_float4(alpha * (a0 + b4.x), alpha * (a1 + b4.y), alpha * (a2 + b4.z), alpha * (a3 + b4.w));
+            y.x = fmaf(beta, xv.x, y.x); y.y = fmaf(beta, xv.y, y.y); y.z = fmaf(beta, xv.z, y.z); y.w = fmaf(beta, xv.w, y.w);
+            return y;
+        };
+        if constexpr (XT) {
+            for (int k = 0; k < my_tiles; ++k) {
+                const int b = k & 1;
+                const int trow = (blockIdx.x + k * gridDim.x) * kTileRows;
+                WS_T(te0);
+                named_sync(kFull + b, 512);
+                WS_T(te1); WS_ADD(0, te1 - te0);
+                if (k == 0 && ew >= 4) named_sync(kPhase, 256);                 // (see below) start half a period late
+                const uint32_t* Hh = Hbuf + (size_t)b * 2 * kTileRows * RS;
+                const uint32_t* Hl = Hh + kTileRows * RS;
+                float acc[MTS][4][4];
+#pragma unroll
+                for (int mt = 0; mt < MTS; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+                if (blk_ok) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int c0 = ks * 8 + t;
+                        uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            bh0[j] = lc_ok ? Wh[c0 * WS + lc + j] : 0u; bh1[j] = lc_ok ? Wh[(c0 + 4) * WS + lc + j] : 0u;
+                            bl0[j] = lc_ok ? Wl[c0 * WS + lc + j] : 0u; bl1[j] = lc_ok ? Wl[(c0 + 4) * WS + lc + j] : 0u;
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < MTS; ++mt) {
+                            uint32_t ah[4], al[4];
+                            const int hr = (mt * 16 + g) * RS + ks * 8 + t;
+                            ah[0] = Hh[hr]; ah[1] = Hh[hr + 8 * RS]; ah[2] = Hh[hr + 4]; ah[3] = Hh[hr + 8 * RS + 4];
+                            al[0] = Hl[hr]; al[1] = Hl[hr + 8 * RS]; al[2] = Hl[hr + 4]; al[3] = Hl[hr + 8 * RS + 4];
+                            // three passes over the four n-tiles: consecutive MMAs never touch the same accumulator
+                            // (a dependent HMMA issues only every ~34 cycles, an independent one every ~17)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mma_tf32(acc[mt][j], ah, bh0[j], bh1[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mma_tf32(acc[mt][j], al, bh0[j], bh1[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mma_tf32(acc[mt][j], ah, bl0[j], bl1[j]);
+                        }
+                    }
+                }
+                WS_T(te2); WS_ADD(1, te2 - te1);
+                // Put the two halves of the expand warps in antiphase: the tensor-core phase of one half then runs
+                // under the store phase of the other instead of both phases alternating for the whole SM.
+                if (k == 0 && ew < 4) named_arrive(kPhase, 256);
+                mbar_wait(smem_addr(&xbar[b]), (uint32_t)(k >> 1) & 1u);       // residual rows of tile k have landed
+                WS_T(te3); WS_ADD(2, te3 - te2);
+                const float* xs = Xs + (size_t)b * kTileRows * XS;
+#pragma unroll
+                for (int mt = 0; mt < MTS; ++mt) {
+                    const int lr0 = mt * 16 + g, lr1 = lr0 + 8;
+                    const int r0 = trow + lr0, r1 = trow + lr1;
+                    if (r0 < n) {
+                        if (o0) stg4_stream(Out + (size_t)r0 * ldo + oc, fin(acc[mt][0][0], acc[mt][1][0], acc[mt][2][0], acc[mt][3][0], b4a,
+                                            *reinterpret_cast<const float4*>(xs + (size_t)lr0 * XS + oc)));
+                        if (o1) stg4_stream(Out + (size_t)r0 * ldo + oc1, fin(acc[mt][0][1], acc[mt][1][1], acc[mt][2][1], acc[mt][3][1], b4b,
+                                            *reinterpret_cast<const float4*>(xs + (size_t)lr0 * XS + oc1)));
+                    }
+                    if (r1 < n) {
+                        if (o0) stg4_stream(Out + (size_t)r1 * ldo + oc, fin(acc[mt][0][2], acc[mt][1][2], acc[mt][2][2], acc[mt][3][2], b4a,
+                                            *reinterpret_cast<const float4*>(xs + (size_t)lr1 * XS + oc)));
+                        if (o1) stg4_stream(Out + (size_t)r1 * ldo + oc1, fin(acc[mt][0][3], acc[mt][1][3], acc[mt][2][3], acc[mt][3][3], b4b,
+                                            *reinterpret_cast<const float4*>(xs + (size_t)lr1 * XS + oc1)));
+                    }
+                }
+                if (k + 2 < my_tiles) named_arrive(kEmpty + b, 512);
+                WS_T(te4); WS_ADD(3, te4 - te3);
+            }
+#ifdef GCA_WS_DEBUG
+            if (warp == 8 && lane == 0) {
+                for (int i = 0; i < 4; ++i) atomicAdd(&g_ws_dbg[i], ws_acc[i]);
+                atomicAdd(&g_ws_dbg[4], clock64() - ws_t0);
+            }
+#endif
+            return;
+        }
         float4 x[MTS][4];                                       // residual of (row g, oc) (row g, oc1) (row g+8, ..)
         auto prefetch = [&](int k, int mt) {
             const int r0 = (blockIdx.x + k * gridDim.x) * kTileRows + mt * 16 + g, r1 = r0 + 8;
@@ -987,11 +1146,6 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                     }
                 }
                 const int r0 = trow + mt * 16 + g, r1 = r0 + 8;
-                auto fin = [&](float a0, float a1, float a2, float a3, const float4& b4, const float4& xv) {
-                    float4 y = make_float4(alpha * (a0 + b4.x), alpha * (a1 + b4.y), alpha * (a2 + b4.z), alpha * (a3 + b4.w));
-                    y.x = fmaf(beta, xv.x, y.x); y.y = fmaf(beta, xv.y, y.y); y.z = fmaf(beta, xv.z, y.z); y.w = fmaf(beta, xv.w, y.w);
-                    return y;
-                };
                 if (r0 < n) {
                     if (o0) stg4_stream(Out + (size_t)r0 * ldo + oc, fin(acc[0][0], acc[1][0], acc[2][0], acc[3][0], b4a, x[mt][0]));
                     if (o1) stg4_stream(Out + (size_t)r0 * ldo + oc1, fin(acc[0][1], acc[1][1], acc[2][1], acc[3][1], b4b, x[mt][1]));
@@ -1594,12 +1748,21 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
             static const int use_ws = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && e[0] == 'm') ? 0 : 1; }();
             const size_t smem_ws = sizeof(uint32_t) * ((size_t)2 * R * (d + 1) + (size_t)4 * kTileRows * (R + 4));
             if (use_ws && Out && d <= 256 && n >= 4 * kTileRows && smem_ws <= 200 * 1024) {
-                GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR>, smem_ws));
                 const int ntiles_w = (n + kTileRows - 1) / kTileRows;
                 const int grid_w = ntiles_w < num_sms() ? ntiles_w : num_sms();
-                {
-                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
-                    GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR>, dim3(grid_w), dim3(512), smem_ws, st, rowptr, colidx, dis, F, W, bias,
+                // residual through bulk copies when it fits next to W and the H tiles (GCA_HOP_EXPAND=r: registers)
+                static const int no_xt = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && e[0] == 'r') ? 1 : 0; }();
+                const size_t smem_xt = smem_ws + 32 + sizeof(float) * (size_t)2 * kTileRows * (d + 16) + 16;
+                const bool xt = !no_xt && use_resid && resid && (ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) % 16) == 0 &&
+                                smem_xt <= 227 * 1024;
+                ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                if (xt) {
+                    GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR, true>, smem_xt));
+                    GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR, true>, dim3(grid_w), dim3(512), smem_xt, st, rowptr, colidx, dis, F, W, bias,
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part));
+                } else {
+                    GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR, false>, smem_ws));
+                    GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR, false>, dim3(grid_w), dim3(512), smem_ws, st, rowptr, colidx, dis, F, W, bias,
                                         resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part));
                 }
                 GCA_LAUNCH_OK();
@@ -1877,6 +2040,15 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
     GCA_LAUNCH_OK();
     return GCA_OK;
 }
+
+#ifdef GCA_WS_DEBUG
+extern "C" int gca_ws_debug_counters(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_ws_dbg, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_ws_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // ---------------- single-GPU conveniences ----------------
 extern "C" size_t gca_forward_workspace_bytes(int32_t n, int32_t d, int32_t r) {
