@@ -15,7 +15,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <cuda.h>
+
 #include "gca_common.cuh"
+#include "gca_tc.cuh"
 
 namespace gca {
 
@@ -1162,6 +1165,304 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 }
 
 // ------------------------------------------------------------------------------------------
+// K3-tc: hop + expand with the expansion on the 5th-generation tensor core (tcgen05, accumulator in TMEM) and
+// all d-wide traffic moved by the bulk-copy engine.  One persistent 512-thread CTA per SM, 128-row tiles:
+//   warps 0-7   gather: the pipelined r-wide SpMM of tile k -> H tile (tf32 hi / lo, UMMA canonical K-major
+//               core-matrix layout) in shared memory, double-buffered; H2 rows also go to global memory.
+//   warp  8     one thread issues the 3 x (R/8) tcgen05.mma.kind::tf32 of a tile: D[128, d] = H_hi W_hi + H_lo W_hi
+//               + H_hi W_lo with W resident in shared memory (K-major, split once per CTA), D in one of two
+//               256-column TMEM stages; tcgen05.commit hands the H buffer back and the accumulator over.
+//   warps 12-15 epilogue: warp q owns TMEM lanes / tile rows 32q..32q+31, lane = row.  Per 64-column chunk:
+//               tcgen05.ld the accumulator, read the residual chunk from this warp's ring slot (filled by a
+//               per-row cp.async.bulk, completion on an mbarrier), y = alpha (acc + b) + beta x in place,
+//               fence.proxy.async, per-row cp.async.bulk store to Y, then refill the previous slot with the
+//               chunk 4 items ahead once its store has drained (wait_group.read).
+// The mma.sync variant spends ~3300 cycles of tensor pipe per 64 rows on the 3xTF32 expansion and as much again
+// in its store phase, serialised per warp (profiles/README.md); here the tensor work is 6 instructions per tile
+// and no d-wide byte passes through a register of a load/store instruction.
+// ------------------------------------------------------------------------------------------
+constexpr int kTcRows = 128;
+constexpr int kTcChunk = 64;                    // columns per epilogue item = two 32-column TMA boxes
+constexpr int kTcSlots = 4;                     // ring slots per epilogue warp
+constexpr int kTcBoxBytes = 32 * 32 * 4;        // one box: 32 rows x 128 bytes, SWIZZLE_128B (1 KB atoms)
+constexpr int kTcSlotBytes = 2 * kTcBoxBytes;
+
+template <int R>
+constexpr size_t hop_expand_tc_smem(int d) {
+    return (size_t)2 * R * d * 4 + (size_t)4 * R * kTcRows * 4 + (size_t)4 * kTcSlots * kTcSlotBytes + (size_t)d * 4 + 32 * 8 + 16 + 1024;
+}
+
+// 2D tiled bulk copies through a tensor map (box = 32 rows x 32 fp32 columns, 128-byte swizzle): one instruction
+// moves 4 KB, rows beyond the tensor are zero-filled on load and clipped on store.
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(tm), "r"(col), "r"(row), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, int col, int row, uint32_t src, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                 ::"l"(tm), "r"(col), "r"(row), "r"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {       // 32 lanes x 32 consecutive columns, no wait
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int R, bool W_IS_DR>
+__global__ void __launch_bounds__(512, 1)
+k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
+                const float* __restrict__ F, const float* __restrict__ W, const float* __restrict__ bias,
+                const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
+                int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
+                int n, int d, const int* __restrict__ hubitem, const float* __restrict__ hub_part,
+                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y) {
+    constexpr int LPG = R / 4, GPW = 32 / LPG;
+    constexpr int SCA = (kTcRows >> 3) * 128;          // bytes between 4-column K chunks of the H tile
+    constexpr int kHPart = R * kTcRows * 4;            // one of {hi, lo} of one H buffer
+    extern __shared__ uint8_t smem_unaligned[];
+    uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
+    const int SCW = (d >> 3) * 128;                    // bytes between 4-column K chunks of W ([d, R], K-major)
+    uint8_t* Wh = smem_raw;
+    uint8_t* Wl = Wh + (size_t)R * d * 4;
+    uint8_t* Hb = Wl + (size_t)R * d * 4;              // [2 buffers][hi, lo][kHPart]
+    uint8_t* Xr = Hb + 4 * kHPart;                     // [4 warps][kTcSlots][2 boxes][32 rows][128 B swizzled]; 1 KB aligned
+    float* bias_s = reinterpret_cast<float*>(Xr + 4 * kTcSlots * kTcSlotBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + d);
+    const uint32_t bar0 = smem_addr(bars);
+    auto hfull = [&](int b) { return bar0 + 8u * b; };
+    auto hempty = [&](int b) { return bar0 + 8u * (2 + b); };
+    auto tfull = [&](int a) { return bar0 + 8u * (4 + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (6 + a); };
+    auto xfull = [&](int q, int s_) { return bar0 + 8u * (8 + q * kTcSlots + s_); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 4 * kTcSlots);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(hfull(b), 8); mbar_init(hempty(b), 1); mbar_init(tfull(b), 1); mbar_init(tempty(b), 4); }
+        for (int i = 0; i < 4 * kTcSlots; ++i) mbar_init(bar0 + 8u * (8 + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tc::tmem_alloc(smem_addr(tmem_slot), 512);
+    // W -> shared, split, canonical K-major layout: element (c, k) -> (k/4) SCW + (c/8) 128 + (c%8) 16 + (k%4) 4
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
+        int k, c;
+        if (W_IS_DR) { c = idx / R; k = idx - c * R; } else { k = idx / d; c = idx - k * d; }
+        uint32_t hi, lo;
+        split_tf32(W[idx], hi, lo);
+        const uint32_t off = (uint32_t)((k >> 2) * SCW + (c >> 3) * 128 + (c & 7) * 16 + (k & 3) * 4);
+        *reinterpret_cast<uint32_t*>(Wh + off) = hi;
+        *reinterpret_cast<uint32_t*>(Wl + off) = lo;
+    }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) bias_s[i] = bias ? bias[i] : 0.f;
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    const int ntiles = (n + kTcRows - 1) / kTcRows;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < 8) {
+        // ===================== gather warps (same software pipeline as K3-ws) =====================
+        const int sub = lane % LPG, grp = lane / LPG;
+        constexpr int PASSES = kTcRows / (8 * GPW);
+        constexpr int kPre = 16;
+        const int nsteps = my_tiles * PASSES;
+        auto row_of = [&](int s_) {
+            const int k_ = s_ / PASSES, ps = s_ - k_ * PASSES;
+            return (blockIdx.x + k_ * (int)gridDim.x) * kTcRows + ps * 8 * GPW + warp * GPW + grp;
+        };
+        struct Meta { int beg, end; float dis; };
+        auto meta_load = [&](int s_) {
+            Meta m{0, 0, 0.f};
+            if (s_ < nsteps) {
+                const int row = row_of(s_);
+                if (row < n) { m.beg = __ldg(rowptr + row); m.end = __ldg(rowptr + row + 1); m.dis = __ldg(dis + row); }
+            }
+            return m;
+        };
+        auto idx_load = [&](const Meta& m, int (&j)[kPre]) {
+            const bool fast = m.end - m.beg <= kLongRow;
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) j[u] = (fast && m.beg + u < m.end) ? __ldg(colidx + m.beg + u) : -1;
+        };
+        Meta m0 = meta_load(0), m1 = meta_load(1);
+        int j0[kPre], j1[kPre];
+        idx_load(m0, j0);
+        for (int s_ = 0; s_ < nsteps; ++s_) {
+            const int k = s_ / PASSES, ps = s_ - k * PASSES, b = k & 1;
+            const Meta m2 = meta_load(s_ + 2);
+            idx_load(m1, j1);
+            float4 v[kPre];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u)
+                v[u] = (j0[u] >= 0) ? ldg4(F + (size_t)j0[u] * R + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) acc = f4_add(acc, v[u]);
+            const int row = row_of(s_);
+            const bool valid = row < n;
+            const int deg = m0.end - m0.beg;
+            const bool is_hub = deg > kHubDeg;
+            const bool is_long = deg > kLongRow && !is_hub;
+            if (is_hub) {
+                acc = hub_row_sum<R>(hub_part, __ldg(hubitem + row), (deg + kHubChunk - 1) / kHubChunk, sub);
+            } else if (!is_long && deg > kPre) {
+                const float4 rest = gather_rows<R>(F, colidx, m0.beg + kPre, m0.end, 1, sub);
+                acc = f4_add(acc, rest);
+            }
+            unsigned longmask = __ballot_sync(0xffffffffu, is_long);
+            while (longmask) {                                   // warp-uniform
+                const int src = __ffs(longmask) - 1;
+                const int g_ = src / LPG;
+                const unsigned gm = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << (g_ * LPG));
+                longmask &= ~gm;
+                const int lb = __shfl_sync(0xffffffffu, m0.beg, src), le = __shfl_sync(0xffffffffu, m0.end, src);
+                float4 part = gather_rows<R>(F, colidx, lb + grp, le, GPW, sub);
+#pragma unroll
+                for (int off = LPG; off < 32; off <<= 1) part = f4_add(part, f4_shfl_xor(part, off));
+                if (grp == g_) acc = part;
+            }
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                h = f4_scale(acc, m0.dis);
+                *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
+            }
+            uint4 hi, lo;
+            split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+            if (ps == 0 && k >= 2) mbar_wait(hempty(b), (uint32_t)(((k >> 1) - 1) & 1));   // MMAs of tile k-2 have retired
+            const int hr = ps * 8 * GPW + warp * GPW + grp;
+            const uint32_t off = (uint32_t)(sub * SCA + (hr >> 3) * 128 + (hr & 7) * 16);
+            *reinterpret_cast<uint4*>(Hb + (size_t)(b * 2) * kHPart + off) = hi;
+            *reinterpret_cast<uint4*>(Hb + (size_t)(b * 2 + 1) * kHPart + off) = lo;
+            if (ps == PASSES - 1) {
+                tc::fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(hfull(b));
+            }
+            m0 = m1; m1 = m2;
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(kTcRows, d, 0, 0);
+            const uint64_t stepA = (uint64_t)((2 * SCA) >> 4), stepB = (uint64_t)((2 * SCW) >> 4);
+            const uint64_t b_hi = tc::make_desc(smem_addr(Wh), (uint32_t)SCW, 128), b_lo = tc::make_desc(smem_addr(Wl), (uint32_t)SCW, 128);
+            for (int k = 0; k < my_tiles; ++k) {
+                const int b = k & 1;
+                mbar_wait(hfull(b), (uint32_t)((k >> 1) & 1));
+                mbar_wait(tempty(b), (uint32_t)(((k >> 1) & 1) ^ 1));
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
+                const uint64_t a_hi = tc::make_desc(smem_addr(Hb + (size_t)(b * 2) * kHPart), SCA, 128);
+                const uint64_t a_lo = tc::make_desc(smem_addr(Hb + (size_t)(b * 2 + 1) * kHPart), SCA, 128);
+#pragma unroll
+                for (int ks = 0; ks < R / 8; ++ks) {
+                    tc::umma_tf32(d_tmem, a_lo + ks * stepA, b_hi + ks * stepB, idesc, ks > 0 ? 1u : 0u);
+                    tc::umma_tf32(d_tmem, a_hi + ks * stepA, b_lo + ks * stepB, idesc, 1u);
+                    tc::umma_tf32(d_tmem, a_hi + ks * stepA, b_hi + ks * stepB, idesc, 1u);
+                }
+                tc::umma_commit(hempty(b));
+                tc::umma_commit(tfull(b));
+            }
+        }
+    } else if (warp >= 12) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const float s = scalar ? __ldg(scalar) : 1.f;
+        const float alpha = alpha_is_scalar ? s : 1.f;
+        const float beta = use_resid ? s : 0.f;
+        const int nchunk = d / kTcChunk;
+        const int total = my_tiles * nchunk;
+        const uint64_t pol = policy_evict_first();
+        uint8_t* myslots = Xr + (size_t)q * kTcSlots * kTcSlotBytes;
+        auto issue_load = [&](int it) {                            // residual chunk of item `it` -> its ring slot (lane 0)
+            const int k_ = it / nchunk, c_ = it - k_ * nchunk, slot = it % kTcSlots;
+            const int row0 = (blockIdx.x + k_ * (int)gridDim.x) * kTcRows + q * 32;
+            const uint32_t dst = smem_addr(myslots + (size_t)slot * kTcSlotBytes);
+            mbar_arrive_expect_tx(xfull(q, slot), (uint32_t)kTcSlotBytes);
+            tma_load_box(dst, &tm_x, c_ * kTcChunk, row0, xfull(q, slot), pol);
+            tma_load_box(dst + kTcBoxBytes, &tm_x, c_ * kTcChunk + 32, row0, xfull(q, slot), pol);
+        };
+        if (use_resid && lane == 0)
+            for (int it = 0; it < kTcSlots && it < total; ++it) issue_load(it);
+        const int sw = lane & 7;                                   // 16-byte chunk j of row `lane` sits at chunk j ^ (lane % 8)
+        int it = 0;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int b = k & 1;
+            const int row0 = (blockIdx.x + k * (int)gridDim.x) * kTcRows + q * 32;
+            mbar_wait(tfull(b), (uint32_t)((k >> 1) & 1));
+            tc::tc_fence_after();
+            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
+            for (int c = 0; c < nchunk; ++c, ++it) {
+                const int slot = it % kTcSlots;
+                float acc[kTcChunk];
+                tmem_ld32(tb + (uint32_t)(c * kTcChunk), acc);
+                tmem_ld32(tb + (uint32_t)(c * kTcChunk + 32), acc + 32);
+                if (use_resid) mbar_wait(xfull(q, slot), (uint32_t)((it / kTcSlots) & 1));
+                tmem_ld_wait();
+                if (c == nchunk - 1) {                              // accumulator stage can be overwritten
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(tempty(b));
+                }
+                uint8_t* slotp = myslots + (size_t)slot * kTcSlotBytes + (size_t)lane * 128;
+                const float4* bs = reinterpret_cast<const float4*>(bias_s + c * kTcChunk);
+#pragma unroll
+                for (int j = 0; j < kTcChunk / 4; ++j) {
+                    float4* xp = reinterpret_cast<float4*>(slotp + (j >> 3) * kTcBoxBytes + (((j & 7) ^ sw) << 4));
+                    const float4 b4 = bs[j];
+                    const float4 x4 = use_resid ? *xp : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 y = make_float4(alpha * (acc[4 * j] + b4.x), alpha * (acc[4 * j + 1] + b4.y), alpha * (acc[4 * j + 2] + b4.z),
+                                           alpha * (acc[4 * j + 3] + b4.w));
+                    y.x = fmaf(beta, x4.x, y.x); y.y = fmaf(beta, x4.y, y.y); y.z = fmaf(beta, x4.z, y.z); y.w = fmaf(beta, x4.w, y.w);
+                    *xp = y;
+                }
+                tc::fence_proxy_async();                           // generic-proxy writes -> visible to the bulk store
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t src = smem_addr(myslots + (size_t)slot * kTcSlotBytes);
+                    tma_store_box(&tm_y, c * kTcChunk, row0, src, pol);
+                    tma_store_box(&tm_y, c * kTcChunk + 32, row0, src + kTcBoxBytes, pol);
+                    bulk_commit();
+                    if (it >= 1) {
+                        bulk_wait_read<1>();                       // the store of item it-1 has left its slot
+                        if (use_resid && it - 1 + kTcSlots < total) issue_load(it - 1 + kTcSlots);
+                    }
+                }
+                __syncwarp();                                       // nobody rewrites a slot before lane 0 saw it drained
+            }
+        }
+        bulk_wait_all();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4-mma: G[c, k] = sum_i H[i, c] A[i, k]  (+ colsum, dot) with M = c, N = k (columns of A), K = rows.
 // CTA = 8 warps = 8 column blocks of 32; every warp sweeps ALL rows of the CTA's tiles for its block, so
 // no cross-warp reduction is needed.  Per 128-row tile the products are accumulated by the tensor core,
@@ -1650,6 +1951,28 @@ int set_smem(K kernel, size_t bytes, bool has_static_smem = false) {
     return GCA_OK;
 }
 
+// Tensor map of a row-major fp32 [rows, cols] matrix with leading dimension ld, box = 32 x 32, 128-byte swizzle.
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
+inline bool make_box_map(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ld) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn enc = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline bool shape_ok(int d, int r) { return d > 0 && (d % 4) == 0 && (r == 8 || r == 16 || r == 32 || r == 64); }
 
 template <int R, bool W_IS_RD>
@@ -1747,6 +2070,26 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
         if (tc_enabled()) {
             static const int use_ws = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && e[0] == 'm') ? 0 : 1; }();
             const size_t smem_ws = sizeof(uint32_t) * ((size_t)2 * R * (d + 1) + (size_t)4 * kTileRows * (R + 4));
+            // tcgen05 + bulk-copy variant (GCA_HOP_EXPAND=w falls back to the mma.sync warp-specialised kernel)
+            static const int no_tc = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && (e[0] == 'w' || e[0] == 'r' || e[0] == 'm')) ? 1 : 0; }();
+            if constexpr (R == 16) {
+                if (!no_tc && Out && d <= 256 && (d % kTcChunk) == 0 && n >= 4 * kTcRows && (ldo % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(Out) % 16) == 0 &&
+                    (!use_resid || (resid && (ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) % 16) == 0))) {
+                    const size_t smem_tc = hop_expand_tc_smem<R>(d);
+                    GCA_TRY(set_smem(k_hop_expand_tc<R, W_IS_DR>, smem_tc));
+                    const int ntiles_t = (n + kTcRows - 1) / kTcRows;
+                    const int grid_t = ntiles_t < num_sms() ? ntiles_t : num_sms();
+                    CUtensorMap tm_x, tm_y;
+                    if (!make_box_map(&tm_y, Out, n, d, ldo) || !make_box_map(&tm_x, use_resid ? resid : Out, n, d, use_resid ? ldr : ldo))
+                        return GCA_ERR_CUDA;
+                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                    GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y));
+                    GCA_LAUNCH_OK();
+                    return GCA_OK;
+                }
+            }
             if (use_ws && Out && d <= 256 && n >= 4 * kTileRows && smem_ws <= 200 * 1024) {
                 const int ntiles_w = (n + kTileRows - 1) / kTileRows;
                 const int grid_w = ntiles_w < num_sms() ? ntiles_w : num_sms();
