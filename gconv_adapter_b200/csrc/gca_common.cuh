@@ -19,7 +19,8 @@ struct gca_graph {
     float* dis;
     int32_t* cnt;      // [n] counters / fill cursors (forward CSR)
     int32_t* cnt_t;    // [n] counters / fill cursors (transposed CSR)
-    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t, [3] hub items, [4] hub items (transpose)
+    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t, [3] hub items, [4] hub items (transpose),
+                       // [5] dynamic tile counter and [6] finished-CTA counter of the kernel currently running on this handle
     // Hub rows (degree > kHubDeg) are cut into work items of kHubChunk neighbours (see gca_graph.cu / k_hub_partials)
     int32_t* hubitem;      // [n]  first item of a hub row, -1 otherwise          (forward CSR)
     int32_t* hubitem_t;    // [n]                                                 (transposed CSR)

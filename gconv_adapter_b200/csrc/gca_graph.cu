@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(1024) k0_build_small(const int64_t* src, const
     const int n = re - rb;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < n; i += nt) { cnt[i] = 0; cnt_t[i] = 0; }
-    if (tid < 5) flags[tid] = 0;
+    if (tid < 8) flags[tid] = 0;
     __syncthreads();
     count_edges(src, dst, E, N, rb, re, normalize, cnt, cnt_t, flags, tid, nt);
     __syncthreads();

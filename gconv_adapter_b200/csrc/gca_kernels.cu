@@ -559,7 +559,7 @@ template <int R, bool W_IS_RD>
 __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
                                                  const float* __restrict__ rowscale, const float* __restrict__ scalar,
                                                  float* __restrict__ out, int n, int d, int bid, int nblocks,
-                                                 uint32_t* smem_u) {
+                                                 uint32_t* smem_u, int* sched = nullptr) {
     constexpr int NT = R / 8;                       // n-tiles
     // The projections are the first kernels of gca_forward / gca_backward: what precedes them on the stream is
     // not ours (an optimizer step may just have written W), so they wait before touching anything.
@@ -589,7 +589,15 @@ __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, in
     const float sc_s = scalar ? __ldg(scalar) : 1.f;
     const int nmt = (n + 15) / 16;                  // 16-row m-tiles
     const int wglobal = bid * 8 + warp, wtotal = nblocks * 8;
-    for (int mt = wglobal; mt < nmt; mt += wtotal) {
+    // m-tiles: the first one is static, the following ones come from a global counter (sched[0]) so that SMs that
+    // stream faster take more of them; the outputs do not depend on which warp computes a tile.
+    int mt = wglobal;
+    while (mt < nmt) {
+        int mt_next = mt + wtotal;
+        if (sched) {
+            if (lane == 0) mt_next = wtotal + atomicAdd(sched, 1);
+            mt_next = __shfl_sync(0xffffffffu, mt_next, 0);
+        }
         const int r0 = mt * 16 + g, r1 = r0 + 8;
         const float* p0 = A + (size_t)min(r0, n - 1) * lda + 4 * t;
         const float* p1 = A + (size_t)min(r1, n - 1) * lda + 4 * t;
@@ -655,15 +663,20 @@ __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, in
             if (r0 < n) *reinterpret_cast<float2*>(out + (size_t)r0 * R + j * 8 + 2 * t) = make_float2(v[0] * sc0, v[1] * sc0);
             if (r1 < n) *reinterpret_cast<float2*>(out + (size_t)r1 * R + j * 8 + 2 * t) = make_float2(v[2] * sc1, v[3] * sc1);
         }
+        mt = mt_next;
+    }
+    if (sched) {                                    // the last CTA to finish re-arms the counters for the next launch
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == nblocks - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
     }
 }
 
 template <int R, bool W_IS_RD>
 __global__ void __launch_bounds__(256, 2)
 k_project_mma(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ rowscale,
-              const float* __restrict__ scalar, float* __restrict__ out, int n, int d) {
+              const float* __restrict__ scalar, float* __restrict__ out, int n, int d, int* sched) {
     extern __shared__ __align__(16) uint32_t smem_dyn[];
-    project_mma_body<R, W_IS_RD>(A, lda, W, rowscale, scalar, out, n, d, blockIdx.x, gridDim.x, smem_dyn);
+    project_mma_body<R, W_IS_RD>(A, lda, W, rowscale, scalar, out, n, d, blockIdx.x, gridDim.x, smem_dyn, sched);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1229,11 +1242,15 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
                 int n, int d, const int* __restrict__ hubitem, const float* __restrict__ hub_part,
                 const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y) {
+#ifdef GCA_WS_DEBUG
+    const long long ws_entry = clock64();
+#endif
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     constexpr int SCA = (kTcRows >> 3) * 128;          // bytes between 4-column K chunks of the H tile
     constexpr int kHPart = R * kTcRows * 4;            // one of {hi, lo} of one H buffer
     extern __shared__ uint8_t smem_unaligned[];
-    uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the array, not an integer round trip, so the accesses stay LDS/STS instead of generic LD/ST)
+    uint8_t* smem_raw = smem_unaligned + ((1024u - (smem_addr(smem_unaligned) & 1023u)) & 1023u);
     const int SCW = (d >> 3) * 128;                    // bytes between 4-column K chunks of W ([d, R], K-major)
     uint8_t* Wh = smem_raw;
     uint8_t* Wl = Wh + (size_t)R * d * 4;
@@ -1278,8 +1295,18 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 
     const int ntiles = (n + kTcRows - 1) / kTcRows;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#ifdef GCA_WS_DEBUG
+    // [0] epi wait-tfull [1] epi wait-xfull [2] epi tmem-ld wait [3] epi math [4] epi fence+store+wait_read+load [5] epi total
+    // [6] gather wait-hempty [7] gather total [8] mma wait-hfull [9] mma wait-tempty [10] mma total
+    long long ws_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long ws_t0 = clock64();
+#endif
 
+#ifdef GCA_EXP_COPYONLY
+    if (false) {
+#else
     if (warp < 8) {
+#endif
         // ===================== gather warps (same software pipeline as K3-ws) =====================
         const int sub = lane % LPG, grp = lane / LPG;
         constexpr int PASSES = kTcRows / (8 * GPW);
@@ -1347,7 +1374,9 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             }
             uint4 hi, lo;
             split_tf32(h.x, hi.x, lo.x); split_tf32(h.y, hi.y, lo.y); split_tf32(h.z, hi.z, lo.z); split_tf32(h.w, hi.w, lo.w);
+            WS_T(g0);
             if (ps == 0 && k >= 2) mbar_wait(hempty(b), (uint32_t)(((k >> 1) - 1) & 1));   // MMAs of tile k-2 have retired
+            WS_T(g1); WS_ADD(6, g1 - g0);
             const int hr = ps * 8 * GPW + warp * GPW + grp;
             const uint32_t off = (uint32_t)(sub * SCA + (hr >> 3) * 128 + (hr & 7) * 16);
             *reinterpret_cast<uint4*>(Hb + (size_t)(b * 2) * kHPart + off) = hi;
@@ -1361,16 +1390,26 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
         }
+#ifdef GCA_WS_DEBUG
+        if (warp == 0 && lane == 0) { atomicAdd(&g_ws_dbg[6], ws_acc[6]); atomicAdd(&g_ws_dbg[7], clock64() - ws_t0); }
+#endif
     } else if (warp == 8) {
         // ===================== MMA issuer =====================
+#ifdef GCA_EXP_COPYONLY
+        if (false) {
+#else
         if (lane == 0) {
+#endif
             const uint32_t idesc = tc::make_idesc_tf32(kTcRows, d, 0, 0);
             const uint64_t stepA = (uint64_t)((2 * SCA) >> 4), stepB = (uint64_t)((2 * SCW) >> 4);
             const uint64_t b_hi = tc::make_desc(smem_addr(Wh), (uint32_t)SCW, 128), b_lo = tc::make_desc(smem_addr(Wl), (uint32_t)SCW, 128);
             for (int k = 0; k < my_tiles; ++k) {
                 const int b = k & 1;
+                WS_T(mm0);
                 mbar_wait(hfull(b), (uint32_t)((k >> 1) & 1));
+                WS_T(mm1); WS_ADD(8, mm1 - mm0);
                 mbar_wait(tempty(b), (uint32_t)(((k >> 1) & 1) ^ 1));
+                WS_T(mm2); WS_ADD(9, mm2 - mm1);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
                 const uint64_t a_hi = tc::make_desc(smem_addr(Hb + (size_t)(b * 2) * kHPart), SCA, 128);
@@ -1384,6 +1423,9 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 tc::umma_commit(hempty(b));
                 tc::umma_commit(tfull(b));
             }
+#ifdef GCA_WS_DEBUG
+            atomicAdd(&g_ws_dbg[8], ws_acc[8]); atomicAdd(&g_ws_dbg[9], ws_acc[9]); atomicAdd(&g_ws_dbg[10], clock64() - ws_t0);
+#endif
         }
     } else if (warp >= 12) {
         // ===================== epilogue =====================
@@ -1410,33 +1452,65 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         for (int k = 0; k < my_tiles; ++k) {
             const int b = k & 1;
             const int row0 = (blockIdx.x + k * (int)gridDim.x) * kTcRows + q * 32;
+            WS_T(e0);
+#ifndef GCA_EXP_COPYONLY
             mbar_wait(tfull(b), (uint32_t)((k >> 1) & 1));
+#endif
+            WS_T(e1); WS_ADD(0, e1 - e0);
             tc::tc_fence_after();
             const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
             for (int c = 0; c < nchunk; ++c, ++it) {
                 const int slot = it % kTcSlots;
                 float acc[kTcChunk];
+#ifdef GCA_EXP_COPYONLY
+#pragma unroll
+                for (int i = 0; i < kTcChunk; ++i) acc[i] = 0.f;
+#else
                 tmem_ld32(tb + (uint32_t)(c * kTcChunk), acc);
                 tmem_ld32(tb + (uint32_t)(c * kTcChunk + 32), acc + 32);
+#endif
+                WS_T(e2);
                 if (use_resid) mbar_wait(xfull(q, slot), (uint32_t)((it / kTcSlots) & 1));
+                WS_T(e3); WS_ADD(1, e3 - e2);
                 tmem_ld_wait();
+                WS_T(e4); WS_ADD(2, e4 - e3);
+#ifndef GCA_EXP_COPYONLY
                 if (c == nchunk - 1) {                              // accumulator stage can be overwritten
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(tempty(b));
                 }
+#endif
                 uint8_t* slotp = myslots + (size_t)slot * kTcSlotBytes + (size_t)lane * 128;
                 const float4* bs = reinterpret_cast<const float4*>(bias_s + c * kTcChunk);
+                // all loads of a half chunk first, then the arithmetic, then the stores: the compiler cannot tell that
+                // the swizzled in-place stores do not alias the later loads and would otherwise serialise them
 #pragma unroll
-                for (int j = 0; j < kTcChunk / 4; ++j) {
-                    float4* xp = reinterpret_cast<float4*>(slotp + (j >> 3) * kTcBoxBytes + (((j & 7) ^ sw) << 4));
-                    const float4 b4 = bs[j];
-                    const float4 x4 = use_resid ? *xp : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 y = make_float4(alpha * (acc[4 * j] + b4.x), alpha * (acc[4 * j + 1] + b4.y), alpha * (acc[4 * j + 2] + b4.z),
-                                           alpha * (acc[4 * j + 3] + b4.w));
-                    y.x = fmaf(beta, x4.x, y.x); y.y = fmaf(beta, x4.y, y.y); y.z = fmaf(beta, x4.z, y.z); y.w = fmaf(beta, x4.w, y.w);
-                    *xp = y;
+                for (int h = 0; h < 4; ++h) {                       // quarter chunks of 16 columns
+                    float4 xv[4], bv[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = h * 4 + jj;
+                        bv[jj] = bs[j];
+                        xv[jj] = use_resid ? *reinterpret_cast<const float4*>(slotp + (j >> 3) * kTcBoxBytes + (((j & 7) ^ sw) << 4))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = h * 4 + jj;
+                        float4 y = make_float4(alpha * (acc[4 * j] + bv[jj].x), alpha * (acc[4 * j + 1] + bv[jj].y),
+                                               alpha * (acc[4 * j + 2] + bv[jj].z), alpha * (acc[4 * j + 3] + bv[jj].w));
+                        y.x = fmaf(beta, xv[jj].x, y.x); y.y = fmaf(beta, xv[jj].y, y.y);
+                        y.z = fmaf(beta, xv[jj].z, y.z); y.w = fmaf(beta, xv[jj].w, y.w);
+                        xv[jj] = y;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = h * 4 + jj;
+                        *reinterpret_cast<float4*>(slotp + (j >> 3) * kTcBoxBytes + (((j & 7) ^ sw) << 4)) = xv[jj];
+                    }
                 }
+                WS_T(e5); WS_ADD(3, e5 - e4);
                 tc::fence_proxy_async();                           // generic-proxy writes -> visible to the bulk store
                 __syncwarp();
                 if (lane == 0) {
@@ -1450,8 +1524,18 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                     }
                 }
                 __syncwarp();                                       // nobody rewrites a slot before lane 0 saw it drained
+                WS_T(e6); WS_ADD(4, e6 - e5);
             }
         }
+#ifdef GCA_WS_DEBUG
+        if (warp == 12 && lane == 0) {
+            for (int i = 0; i < 5; ++i) atomicAdd(&g_ws_dbg[i], ws_acc[i]);
+            const long long tl = clock64() - ws_t0;
+            atomicAdd(&g_ws_dbg[5], tl);
+            atomicMax(&g_ws_dbg[11], (unsigned long long)tl);
+            atomicAdd(&g_ws_dbg[12], (unsigned long long)(ws_t0 - ws_entry));
+        }
+#endif
         bulk_wait_all();
     }
     tc::tc_fence_before();
@@ -1460,6 +1544,13 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+#ifdef GCA_WS_DEBUG
+    if (threadIdx.x == 0) {
+        const long long tt = clock64() - ws_entry;
+        atomicAdd(&g_ws_dbg[13], (unsigned long long)tt);
+        atomicMax(&g_ws_dbg[14], (unsigned long long)tt);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1973,11 +2064,13 @@ inline bool make_box_map(CUtensorMap* tm, const float* base, int rows, int cols,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+inline bool sched_enabled() { static const bool on = [] { const char* e = getenv("GCA_STATIC_SCHED"); return !(e && e[0] == '1'); }(); return on; }
+
 inline bool shape_ok(int d, int r) { return d > 0 && (d % 4) == 0 && (r == 8 || r == 16 || r == 32 || r == 64); }
 
 template <int R, bool W_IS_RD>
 int launch_project(const float* A, int64_t lda, const float* W, const float* rowscale, const float* scalar,
-                   float* out, int n, int d, cudaStream_t st) {
+                   float* out, int n, int d, cudaStream_t st, int* sched = nullptr) {
     if (n == 0) return GCA_OK;
     if (tc_enabled()) {
         // two tensor-core variants: tcgen05 (UMMA + TMEM, shared-memory operand pipeline) and register-level
@@ -1994,7 +2087,7 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
                     if (grid_m > 2 * num_sms()) grid_m = 2 * num_sms();
                     {
                         ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
-                        GCA_CUDA(launch_pdl(k_project_mma<R, W_IS_RD>, dim3(grid_m), dim3(256), smem_m, st, A, lda, W, rowscale, scalar, out, n, d));
+                        GCA_CUDA(launch_pdl(k_project_mma<R, W_IS_RD>, dim3(grid_m), dim3(256), smem_m, st, A, lda, W, rowscale, scalar, out, n, d, sched_enabled() ? sched : nullptr));
                     }
                     GCA_LAUNCH_OK();
                     return GCA_OK;
@@ -2222,7 +2315,7 @@ extern "C" int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, 
     if (!shape_ok(d, r) || (ldx % 4) != 0) return GCA_ERR_UNSUPPORTED;
     const int n = g->row_end - g->row_begin;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GCA_DISPATCH_R(r, (launch_project<R_, true>(X, ldx, Wd, g->dis, nullptr, Pp_local, n, d, st)));
+    GCA_DISPATCH_R(r, (launch_project<R_, true>(X, ldx, Wd, g->dis, nullptr, Pp_local, n, d, st, g->flags + 5)));
 }
 
 extern "C" int gca_fwd_hop1(const gca_graph* g, const float* Pp_full, const float* bd, int act, float* Zp_local,
@@ -2288,7 +2381,7 @@ int bwd_up_impl(const gca_graph* g, const float* gY, int64_t ldg, const float* H
             return GCA_OK;
         }
     }
-    GCA_TRY((launch_project<R, false>(gY, ldg, Wu, g->dis, scalar, gH2p, n, d, st)));
+    GCA_TRY((launch_project<R, false>(gY, ldg, Wu, g->dis, scalar, gH2p, n, d, st, g->flags + 5)));
     return launch_wgrad<R>(gY, ldg, H2, nullptr, 0, S.gu, S.col, nullptr, S.header, 0, n, d, st);
 }
 
@@ -2326,7 +2419,7 @@ extern "C" int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t l
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Scratch S = scratch_ptrs(scratch, d, r);
     GCA_CUDA(cudaMemsetAsync(S.header, 0, 256, st));
-    GCA_DISPATCH_R(r, (launch_project<R_, false>(gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, st)));
+    GCA_DISPATCH_R(r, (launch_project<R_, false>(gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, st, g->flags + 5)));
 }
 
 extern "C" int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, void* scratch,

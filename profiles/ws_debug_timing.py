@@ -44,6 +44,11 @@ raw.gca_ws_debug_counters(buf, 1)
 ctas = 148
 names = ["expand wait-FULL", "expand MMA issue", "expand wait residual", "expand epilogue+stores", "expand total",
          "gather wait-EMPTY", "gather total"]
+if os.environ.get("GCA_HOP_EXPAND", "") == "":      # tcgen05 kernel: different slots
+    names = ["epi wait-tfull", "epi wait-xfull", "epi tmem-ld wait", "epi math (LDS/FMA/STS)", "epi fence+store+wait_read+load",
+             "epi total", "gather wait-hempty", "gather total", "mma wait-hfull", "mma wait-tempty", "mma total",
+             "MAX epi total (x reps x ctas)", "prologue (entry -> loop start)", "CTA lifetime", "MAX CTA lifetime (x reps x ctas)"]
 print("kernel us:", t0.elapsed_time(t1) * 1e3 / reps)
 for i, nm in enumerate(names):
-    print(f"{nm:24s} {buf[i] / reps / ctas:12.0f} cycles per CTA per launch")
+    val = buf[i] if nm.startswith("MAX") else buf[i] / reps / ctas
+    print(f"{nm:36s} {val:12.0f} cycles" + ("" if nm.startswith("MAX") else " per CTA per launch"))
