@@ -1197,12 +1197,13 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 constexpr int kTcRows = 128;
 constexpr int kTcChunk = 64;                    // columns per epilogue item = two 32-column TMA boxes
 constexpr int kTcSlots = 4;                     // ring slots per epilogue warp
+constexpr int kTcQ = 8;                         // entries of the per-CTA tile queue
 constexpr int kTcBoxBytes = 32 * 32 * 4;        // one box: 32 rows x 128 bytes, SWIZZLE_128B (1 KB atoms)
 constexpr int kTcSlotBytes = 2 * kTcBoxBytes;
 
 template <int R>
 constexpr size_t hop_expand_tc_smem(int d) {
-    return (size_t)2 * R * d * 4 + (size_t)4 * R * kTcRows * 4 + (size_t)4 * kTcSlots * kTcSlotBytes + (size_t)d * 4 + 32 * 8 + 16 + 1024;
+    return (size_t)2 * R * d * 4 + (size_t)4 * R * kTcRows * 4 + (size_t)4 * kTcSlots * kTcSlotBytes + (size_t)d * 4 + 64 * 8 + 64 + 1024;
 }
 
 // 2D tiled bulk copies through a tensor map (box = 32 rows x 32 fp32 columns, 128-byte swizzle): one instruction
@@ -1241,7 +1242,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
                 int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
                 int n, int d, const int* __restrict__ hubitem, const float* __restrict__ hub_part,
-                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y) {
+                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, int* sched) {
 #ifdef GCA_WS_DEBUG
     const long long ws_entry = clock64();
 #endif
@@ -1264,25 +1265,46 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
     auto tfull = [&](int a) { return bar0 + 8u * (4 + a); };
     auto tempty = [&](int a) { return bar0 + 8u * (6 + a); };
     auto xfull = [&](int q, int s_) { return bar0 + 8u * (8 + q * kTcSlots + s_); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 4 * kTcSlots);
+    // tile queue: the scheduler thread (warp 9) publishes the CTA's tile sequence, the 13 consumer warps read it
+    auto qfull = [&](int i) { return bar0 + 8u * (8 + 4 * kTcSlots + i); };
+    auto qempty = [&](int i) { return bar0 + 8u * (8 + 4 * kTcSlots + kTcQ + i); };
+    int* tileq = reinterpret_cast<int*>(bars + 8 + 4 * kTcSlots + 2 * kTcQ);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tileq + kTcQ);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) { mbar_init(hfull(b), 8); mbar_init(hempty(b), 1); mbar_init(tfull(b), 1); mbar_init(tempty(b), 4); }
         for (int i = 0; i < 4 * kTcSlots; ++i) mbar_init(bar0 + 8u * (8 + i), 1);
+        for (int i = 0; i < kTcQ; ++i) { mbar_init(qfull(i), 1); mbar_init(qempty(i), 13); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) tc::tmem_alloc(smem_addr(tmem_slot), 512);
     // W -> shared, split, canonical K-major layout: element (c, k) -> (k/4) SCW + (c/8) 128 + (c%8) 16 + (k%4) 4
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < d * R; idx += blockDim.x) {
-        int k, c;
-        if (W_IS_DR) { c = idx / R; k = idx - c * R; } else { k = idx / d; c = idx - k * d; }
-        uint32_t hi, lo;
-        split_tf32(W[idx], hi, lo);
-        const uint32_t off = (uint32_t)((k >> 2) * SCW + (c >> 3) * 128 + (c & 7) * 16 + (k & 3) * 4);
-        *reinterpret_cast<uint32_t*>(Wh + off) = hi;
-        *reinterpret_cast<uint32_t*>(Wl + off) = lo;
+    // (128-bit loads, all of a thread's loads in flight together: the prologue is not hidden behind anything when
+    // the previous kernel's CTA still owns the shared memory of this SM)
+#pragma unroll 2
+    for (int idx4 = threadIdx.x; idx4 < (d * R) / 4; idx4 += blockDim.x) {
+        const int idx = idx4 * 4;
+        const float4 w4 = ldg4(W + idx);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(wv[e], hi[e], lo[e]);
+        if (W_IS_DR) {                                  // 4 consecutive k of one output column c: one 16-byte slot
+            const int c = idx / R, k = idx - c * R;
+            const uint32_t off = (uint32_t)((k >> 2) * SCW + (c >> 3) * 128 + (c & 7) * 16);
+            *reinterpret_cast<uint4*>(Wh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(Wl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else {                                        // 4 consecutive columns c of one k
+            const int k = idx / d, c0 = idx - k * d;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = c0 + e;
+                const uint32_t off = (uint32_t)((k >> 2) * SCW + (c >> 3) * 128 + (c & 7) * 16 + (k & 3) * 4);
+                *reinterpret_cast<uint32_t*>(Wh + off) = hi[e];
+                *reinterpret_cast<uint32_t*>(Wl + off) = lo[e];
+            }
+        }
     }
     for (int i = threadIdx.x; i < d; i += blockDim.x) bias_s[i] = bias ? bias[i] : 0.f;
     tc::fence_proxy_async();
@@ -1294,7 +1316,14 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
     pdl_trigger();
 
     const int ntiles = (n + kTcRows - 1) / kTcRows;
-    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // i-th tile of this CTA (or -1 after the last one); every consumer warp calls this exactly once per i, in order
+    auto get_tile = [&](int i) {
+        mbar_wait(qfull(i % kTcQ), (uint32_t)((i / kTcQ) & 1));
+        const int t_ = tileq[i % kTcQ];
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(qempty(i % kTcQ));
+        return t_;
+    };
 #ifdef GCA_WS_DEBUG
     // [0] epi wait-tfull [1] epi wait-xfull [2] epi tmem-ld wait [3] epi math [4] epi fence+store+wait_read+load [5] epi total
     // [6] gather wait-hempty [7] gather total [8] mma wait-hfull [9] mma wait-tempty [10] mma total
@@ -1311,16 +1340,14 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         const int sub = lane % LPG, grp = lane / LPG;
         constexpr int PASSES = kTcRows / (8 * GPW);
         constexpr int kPre = 16;
-        const int nsteps = my_tiles * PASSES;
-        auto row_of = [&](int s_) {
-            const int k_ = s_ / PASSES, ps = s_ - k_ * PASSES;
-            return (blockIdx.x + k_ * (int)gridDim.x) * kTcRows + ps * 8 * GPW + warp * GPW + grp;
-        };
+        static_assert(PASSES >= 2, "the look-ahead below assumes that steps s .. s+2 span at most two tiles");
+        int tk = get_tile(0), tk1 = tk >= 0 ? get_tile(1) : -1;    // tiles of step s and of the tile after it
+        auto row_in = [&](int tile, int ps) { return tile * kTcRows + ps * 8 * GPW + warp * GPW + grp; };
         struct Meta { int beg, end; float dis; };
-        auto meta_load = [&](int s_) {
+        auto meta_load = [&](int tile, int ps) {
             Meta m{0, 0, 0.f};
-            if (s_ < nsteps) {
-                const int row = row_of(s_);
+            if (tile >= 0) {
+                const int row = row_in(tile, ps);
                 if (row < n) { m.beg = __ldg(rowptr + row); m.end = __ldg(rowptr + row + 1); m.dis = __ldg(dis + row); }
             }
             return m;
@@ -1330,12 +1357,13 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j[u] = (fast && m.beg + u < m.end) ? __ldg(colidx + m.beg + u) : -1;
         };
-        Meta m0 = meta_load(0), m1 = meta_load(1);
+        Meta m0 = meta_load(tk, 0), m1 = meta_load(tk, 1);
         int j0[kPre], j1[kPre];
         idx_load(m0, j0);
-        for (int s_ = 0; s_ < nsteps; ++s_) {
+        for (int s_ = 0; tk >= 0; ++s_) {
             const int k = s_ / PASSES, ps = s_ - k * PASSES, b = k & 1;
-            const Meta m2 = meta_load(s_ + 2);
+            // step s+2: pass ps+2 of this tile, or pass ps+2-PASSES of the next one
+            const Meta m2 = ps + 2 < PASSES ? meta_load(tk, ps + 2) : meta_load(tk1, ps + 2 - PASSES);
             idx_load(m1, j1);
             float4 v[kPre];
 #pragma unroll
@@ -1344,7 +1372,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < kPre; ++u) acc = f4_add(acc, v[u]);
-            const int row = row_of(s_);
+            const int row = row_in(tk, ps);
             const bool valid = row < n;
             const int deg = m0.end - m0.beg;
             const bool is_hub = deg > kHubDeg;
@@ -1389,6 +1417,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             m0 = m1; m1 = m2;
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
+            if (ps == PASSES - 1) { tk = tk1; tk1 = tk >= 0 ? get_tile(k + 2) : -1; }
         }
 #ifdef GCA_WS_DEBUG
         if (warp == 0 && lane == 0) { atomicAdd(&g_ws_dbg[6], ws_acc[6]); atomicAdd(&g_ws_dbg[7], clock64() - ws_t0); }
@@ -1403,7 +1432,12 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             const uint32_t idesc = tc::make_idesc_tf32(kTcRows, d, 0, 0);
             const uint64_t stepA = (uint64_t)((2 * SCA) >> 4), stepB = (uint64_t)((2 * SCW) >> 4);
             const uint64_t b_hi = tc::make_desc(smem_addr(Wh), (uint32_t)SCW, 128), b_lo = tc::make_desc(smem_addr(Wl), (uint32_t)SCW, 128);
-            for (int k = 0; k < my_tiles; ++k) {
+            for (int k = 0;; ++k) {
+                // (lane 0 only: the queue hand-shake is done by hand instead of get_tile's warp-wide version)
+                mbar_wait(qfull(k % kTcQ), (uint32_t)((k / kTcQ) & 1));
+                const int tile_k = tileq[k % kTcQ];
+                tc::mbar_arrive(qempty(k % kTcQ));
+                if (tile_k < 0) break;
                 const int b = k & 1;
                 WS_T(mm0);
                 mbar_wait(hfull(b), (uint32_t)((k >> 1) & 1));
@@ -1427,6 +1461,21 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
             atomicAdd(&g_ws_dbg[8], ws_acc[8]); atomicAdd(&g_ws_dbg[9], ws_acc[9]); atomicAdd(&g_ws_dbg[10], clock64() - ws_t0);
 #endif
         }
+    } else if (warp == 9) {
+        // ===================== tile scheduler =====================
+        // The first tile is static; the following ones come from a global counter, so SMs that get through their
+        // tiles faster (the d-wide streams do not run at the same speed on every SM) take more of them.
+        if (lane == 0) {
+            for (int i = 0;; ++i) {
+                int t_ = i == 0 ? (int)blockIdx.x
+                                : (sched ? (int)gridDim.x + atomicAdd(sched, 1) : (int)blockIdx.x + i * (int)gridDim.x);
+                if (t_ >= ntiles) t_ = -1;
+                if (i >= kTcQ) mbar_wait(qempty(i % kTcQ), (uint32_t)(((i / kTcQ) - 1) & 1));
+                tileq[i % kTcQ] = t_;
+                tc::mbar_arrive(qfull(i % kTcQ));                   // release: consumers acquire through their wait
+                if (t_ < 0) break;
+            }
+        }
     } else if (warp >= 12) {
         // ===================== epilogue =====================
         const int q = warp & 3;
@@ -1434,24 +1483,25 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         const float alpha = alpha_is_scalar ? s : 1.f;
         const float beta = use_resid ? s : 0.f;
         const int nchunk = d / kTcChunk;
-        const int total = my_tiles * nchunk;
+        const int lead = nchunk < kTcSlots - 1 ? nchunk : kTcSlots - 1;   // items between a chunk's load and its use
         const uint64_t pol = policy_evict_first();
         uint8_t* myslots = Xr + (size_t)q * kTcSlots * kTcSlotBytes;
-        auto issue_load = [&](int it) {                            // residual chunk of item `it` -> its ring slot (lane 0)
-            const int k_ = it / nchunk, c_ = it - k_ * nchunk, slot = it % kTcSlots;
-            const int row0 = (blockIdx.x + k_ * (int)gridDim.x) * kTcRows + q * 32;
+        int tk = get_tile(0), tk1 = tk >= 0 ? get_tile(1) : -1;    // this tile and the next one (loads run ahead into it)
+        auto issue_load = [&](int tile, int c_, int it_) {         // residual chunk c_ of `tile` = item it_ -> ring slot (lane 0)
+            const int slot = it_ % kTcSlots;
+            const int row0 = tile * kTcRows + q * 32;
             const uint32_t dst = smem_addr(myslots + (size_t)slot * kTcSlotBytes);
             mbar_arrive_expect_tx(xfull(q, slot), (uint32_t)kTcSlotBytes);
             tma_load_box(dst, &tm_x, c_ * kTcChunk, row0, xfull(q, slot), pol);
             tma_load_box(dst + kTcBoxBytes, &tm_x, c_ * kTcChunk + 32, row0, xfull(q, slot), pol);
         };
-        if (use_resid && lane == 0)
-            for (int it = 0; it < kTcSlots && it < total; ++it) issue_load(it);
+        if (use_resid && lane == 0 && tk >= 0)
+            for (int c_ = 0; c_ < lead; ++c_) issue_load(tk, c_, c_);
         const int sw = lane & 7;                                   // 16-byte chunk j of row `lane` sits at chunk j ^ (lane % 8)
         int it = 0;
-        for (int k = 0; k < my_tiles; ++k) {
+        for (int k = 0; tk >= 0; ++k) {
             const int b = k & 1;
-            const int row0 = (blockIdx.x + k * (int)gridDim.x) * kTcRows + q * 32;
+            const int row0 = tk * kTcRows + q * 32;
             WS_T(e0);
 #ifndef GCA_EXP_COPYONLY
             mbar_wait(tfull(b), (uint32_t)((k >> 1) & 1));
@@ -1518,14 +1568,19 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                     tma_store_box(&tm_y, c * kTcChunk, row0, src, pol);
                     tma_store_box(&tm_y, c * kTcChunk + 32, row0, src + kTcBoxBytes, pol);
                     bulk_commit();
-                    if (it >= 1) {
-                        bulk_wait_read<1>();                       // the store of item it-1 has left its slot
-                        if (use_resid && it - 1 + kTcSlots < total) issue_load(it - 1 + kTcSlots);
+                    if (it >= 1) bulk_wait_read<1>();              // the store of item it-1 has left its slot ...
+                    if (use_resid) {                               // ... which item it+lead may now be loaded into
+                        int cn = c + lead;
+                        const int tile_n = cn < nchunk ? tk : tk1;
+                        if (cn >= nchunk) cn -= nchunk;
+                        if (tile_n >= 0) issue_load(tile_n, cn, it + lead);
                     }
                 }
                 __syncwarp();                                       // nobody rewrites a slot before lane 0 saw it drained
                 WS_T(e6); WS_ADD(4, e6 - e5);
             }
+            tk = tk1;
+            tk1 = tk >= 0 ? get_tile(k + 2) : -1;
         }
 #ifdef GCA_WS_DEBUG
         if (warp == 12 && lane == 0) {
@@ -1544,6 +1599,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+    if (sched && threadIdx.x == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 #ifdef GCA_WS_DEBUG
     if (threadIdx.x == 0) {
         const long long tt = clock64() - ws_entry;
@@ -2115,10 +2171,11 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
 struct Csr {
     const int* rowptr; const int* colidx; const float* dis;
     const int* hubitem; const int* item_row; const int* nitems_ptr; float* hub_part; int nitems_host;
+    int* sched;   // [0] dynamic tile counter, [1] finished-CTA counter (self-resetting, one kernel at a time per handle)
 };
 inline Csr csr_of(const gca_graph* g, bool transpose) {
-    return transpose ? Csr{g->rowptr_t, g->colidx_t, g->dis, g->hubitem_t, g->item_row_t, g->flags + 4, g->hub_part, g->nitems_t}
-                     : Csr{g->rowptr, g->colidx, g->dis, g->hubitem, g->item_row, g->flags + 3, g->hub_part, g->nitems};
+    return transpose ? Csr{g->rowptr_t, g->colidx_t, g->dis, g->hubitem_t, g->item_row_t, g->flags + 4, g->hub_part, g->nitems_t, g->flags + 5}
+                     : Csr{g->rowptr, g->colidx, g->dis, g->hubitem, g->item_row, g->flags + 3, g->hub_part, g->nitems, g->flags + 5};
 }
 // Partial sums of the hub rows over operand F (skipped when the validated build found no hub row).
 template <int R>
@@ -2173,12 +2230,16 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                     GCA_TRY(set_smem(k_hop_expand_tc<R, W_IS_DR>, smem_tc));
                     const int ntiles_t = (n + kTcRows - 1) / kTcRows;
                     const int grid_t = ntiles_t < num_sms() ? ntiles_t : num_sms();
+                    // the per-CTA tile queue can be fed from a global counter (GCA_TC_DYNAMIC=1); measured slower than the
+                    // static round-robin sequence (81 vs 76 us: the last tiles are handed out one by one), so it is off
+                    static const bool tc_dynamic = [] { const char* e = getenv("GCA_TC_DYNAMIC"); return e && e[0] == '1'; }();
                     CUtensorMap tm_x, tm_y;
                     if (!make_box_map(&tm_y, Out, n, d, ldo) || !make_box_map(&tm_x, use_resid ? resid : Out, n, d, use_resid ? ldr : ldo))
                         return GCA_ERR_CUDA;
                     ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
                     GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
-                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y));
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y,
+                                        tc_dynamic ? c.sched : nullptr));
                     GCA_LAUNCH_OK();
                     return GCA_OK;
                 }
