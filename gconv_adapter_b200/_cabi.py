@@ -41,6 +41,7 @@ SIGNATURES = {
     "gca_graph_destroy": (None, [_f]),
     "gca_graph_get_view": (C.c_int, [_f, C.POINTER(GraphView)]),
     "gca_graph_edge_coef": (C.c_int, [_f, _f, _f]),
+    "gca_propagate": (C.c_int, [_f, C.c_int, _f, _i64, _f, _i64, _i32, _f]),
     "gca_fwd_project": (C.c_int, [_f, _f, _i64, _f, _f, _i32, _i32, _f]),
     "gca_fwd_hop1": (C.c_int, [_f, _f, _f, C.c_int, _f, _f, _i32, _f]),
     "gca_fwd_hop2_up": (C.c_int, [_f, _f, _f, _i64, _f, _f, _f, C.c_int, _f, _f, _i64, _i32, _i32, _f]),

@@ -97,6 +97,16 @@ int    gca_graph_get_view(const gca_graph* g, gca_graph_view* out /* host */);
  * edge weights gcn_norm would produce.  Only valid for a full-graph handle (n == N). */
 int    gca_graph_edge_coef(const gca_graph* g, float* coef, gca_stream_t stream);
 
+/* -------- backbone propagation over the same handle --------
+ * out[i, 0:D] = dis[i] * sum_{j in N(i)} dis[j] * X[j, 0:D]  for the handle's local rows; transpose = 1 uses the
+ * CSR by source (the adjoint: the backward of transpose = 0).  For a graph that already contains exactly one self loop
+ * per node this is DIFFormer's gcn_conv (src/models/transductive/difformer.py:63-79, edge_weight = None) and the
+ * aggregation of NodeFormer's add_conv_relational_bias (src/models/transductive/nodeformer.py:202-224) with the heads
+ * flattened into D; coefficients differ from the reference's sqrt(1/d) products by <= 2 ULP.  D % 4 == 0; full-graph
+ * handles only (row_begin = 0, row_end = N). */
+int gca_propagate(const gca_graph* g, int transpose, const float* X_full /*[N,D]*/, int64_t ldx,
+                  float* out_local /*[n,D]*/, int64_t ldo, int32_t D, gca_stream_t stream);
+
 /* -------- forward phases (src/finetune/gconv_adapter.py:92-106) --------
  * n = local rows.  *_full buffers hold all N rows (after the caller's all-gather);
  * *_local buffers hold the n local rows.  On one GPU they are the same buffer.
