@@ -265,7 +265,7 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
       const float* __restrict__ F, const float* __restrict__ bias, int act,
       const float* __restrict__ Zp_saved, const float* __restrict__ H1_saved,
       float* __restrict__ out, float* __restrict__ H1_out, float* __restrict__ part_bd, int* header, int n,
-      const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
+      const int* __restrict__ hubitem, const float* __restrict__ hub_part, int plain) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPG, grp = lane / LPG;
@@ -283,6 +283,10 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
         const float di = __ldg(dis + row);
         const size_t o = (size_t)row * R + sub * 4;
         if (!BWD) {
+            if (plain) {                                   // just the hop: out = dis * (A' F)  (first half of a split K3)
+                *reinterpret_cast<float4*>(out + o) = f4_scale(acc, di);
+                continue;
+            }
             float4 h = make_float4(fmaf(di, acc.x, b4.x), fmaf(di, acc.y, b4.y), fmaf(di, acc.z, b4.z), fmaf(di, acc.w, b4.w));
             if (H1_out) *reinterpret_cast<float4*>(H1_out + o) = h;
             h = make_float4(act_apply(h.x, act), act_apply(h.y, act), act_apply(h.z, act), act_apply(h.w, act));
@@ -876,7 +880,7 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
                 int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
                 int n, int d,
-    const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
+    const int* __restrict__ hubitem, const float* __restrict__ hub_part, int pregathered) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     constexpr int RS = R + 4;
     constexpr int KS = R / 8;
@@ -934,7 +938,7 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         struct Meta { int beg, end; float dis; };
         auto meta_load = [&](int s_) {
             Meta m{0, 0, 0.f};
-            if (s_ < nsteps) {
+            if (s_ < nsteps && !pregathered) {
                 const int row = row_of(s_);
                 if (row < n) { m.beg = __ldg(rowptr + row); m.end = __ldg(rowptr + row + 1); m.dis = __ldg(dis + row); }
             }
@@ -945,11 +949,23 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j[u] = (fast && m.beg + u < m.end) ? __ldg(colidx + m.beg + u) : -1;
         };
+        // pregathered = 1 (second half of a split K3): H was already produced by a plain hop kernel; the warps only
+        // stage their rows of it (loaded two steps ahead) and keep the buffer / residual hand-shakes
+        auto hrow_load = [&](int s_) {
+            float4 h_ = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pregathered && s_ < nsteps) {
+                const int row = row_of(s_);
+                if (row < n) h_ = ldg4(Hout + (size_t)row * R + sub * 4);
+            }
+            return h_;
+        };
+        float4 hp0 = hrow_load(0), hp1 = hrow_load(1);
         Meta m0 = meta_load(0), m1 = meta_load(1);
         int j0[kPre], j1[kPre];
         idx_load(m0, j0);
         for (int s_ = 0; s_ < nsteps; ++s_) {
             const int k = s_ / PASSES, ps = s_ - k * PASSES, b = k & 1;
+            const float4 hp2 = hrow_load(s_ + 2);
             const Meta m2 = meta_load(s_ + 2);
             idx_load(m1, j1);
             float4 v[kPre];
@@ -983,7 +999,9 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 if (grp == g_) acc = part;
             }
             float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
+            if (pregathered) {
+                h = hp0;
+            } else if (valid) {
                 h = f4_scale(acc, m0.dis);
                 *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
             }
@@ -1012,6 +1030,7 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 named_arrive(kFull + b, 512);
             }
             m0 = m1; m1 = m2;
+            hp0 = hp1; hp1 = hp2;
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
         }
@@ -2172,10 +2191,11 @@ struct Csr {
     const int* rowptr; const int* colidx; const float* dis;
     const int* hubitem; const int* item_row; const int* nitems_ptr; float* hub_part; int nitems_host;
     int* sched;   // [0] dynamic tile counter, [1] finished-CTA counter (self-resetting, one kernel at a time per handle)
+    int n_full;   // rows of the gathered operand (all N nodes)
 };
 inline Csr csr_of(const gca_graph* g, bool transpose) {
-    return transpose ? Csr{g->rowptr_t, g->colidx_t, g->dis, g->hubitem_t, g->item_row_t, g->flags + 4, g->hub_part, g->nitems_t, g->flags + 5}
-                     : Csr{g->rowptr, g->colidx, g->dis, g->hubitem, g->item_row, g->flags + 3, g->hub_part, g->nitems, g->flags + 5};
+    return transpose ? Csr{g->rowptr_t, g->colidx_t, g->dis, g->hubitem_t, g->item_row_t, g->flags + 4, g->hub_part, g->nitems_t, g->flags + 5, g->N}
+                     : Csr{g->rowptr, g->colidx, g->dis, g->hubitem, g->item_row, g->flags + 3, g->hub_part, g->nitems, g->flags + 5, g->N};
 }
 // Partial sums of the hub rows over operand F (skipped when the validated build found no hub row).
 template <int R>
@@ -2193,7 +2213,8 @@ int launch_hub_partials(const Csr& c, const float* F, cudaStream_t st) {
 
 template <int R, bool BWD>
 int launch_hop(const Csr& c, const float* F, const float* bias, int act,
-               const float* Zp, const float* H1s, float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st) {
+               const float* Zp, const float* H1s, float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st,
+               int plain = 0, const char* prof_name = nullptr) {
     constexpr int GPW = 32 / (R / 4);
     GCA_TRY(launch_hub_partials<R>(c, F, st));
     const int* rowptr = c.rowptr; const int* colidx = c.colidx; const float* dis = c.dis;
@@ -2202,8 +2223,8 @@ int launch_hop(const Csr& c, const float* F, const float* bias, int act,
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     {
-        ProfScope ps(BWD ? "hop_bwd" : "hop_fwd", st);
-        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, c.hubitem, c.hub_part));
+        ProfScope ps(prof_name ? prof_name : (BWD ? "hop_bwd" : "hop_fwd"), st);
+        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, c.hubitem, c.hub_part, plain));
     }
     GCA_LAUNCH_OK();
     return GCA_OK;
@@ -2245,6 +2266,14 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                 }
             }
             if (use_ws && Out && d <= 256 && n >= 4 * kTileRows && smem_ws <= 200 * 1024) {
+                // When the gathered operand is far larger than L2 the neighbour rows come from HBM and the 8 gather warps
+                // of the fused kernel cannot keep enough of them in flight: run the hop as its own high-occupancy kernel
+                // (k_hop, plain mode: 64 warps per SM) and let the fused kernel only expand the H it left in global memory.
+                static const long long split_bytes = [] { const char* e = getenv("GCA_SPLIT_MB"); return (e ? atoll(e) : 160LL) << 20; }();
+                const int pregathered = (long long)c.n_full * R * 4 > split_bytes ? 1 : 0;
+                if (pregathered)
+                    GCA_TRY((launch_hop<R, false>(c, F, nullptr, GCA_ACT_NONE, nullptr, nullptr, Hout, nullptr, nullptr, nullptr, n, st, 1,
+                                                  W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd")));
                 const int ntiles_w = (n + kTileRows - 1) / kTileRows;
                 const int grid_w = ntiles_w < num_sms() ? ntiles_w : num_sms();
                 // residual through bulk copies when it fits next to W and the H tiles (GCA_HOP_EXPAND=r: registers)
@@ -2256,11 +2285,11 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                 if (xt) {
                     GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR, true>, smem_xt));
                     GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR, true>, dim3(grid_w), dim3(512), smem_xt, st, rowptr, colidx, dis, F, W, bias,
-                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part));
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, pregathered));
                 } else {
                     GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR, false>, smem_ws));
                     GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR, false>, dim3(grid_w), dim3(512), smem_ws, st, rowptr, colidx, dis, F, W, bias,
-                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part));
+                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, pregathered));
                 }
                 GCA_LAUNCH_OK();
                 return GCA_OK;
