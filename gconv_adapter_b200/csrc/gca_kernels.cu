@@ -1215,14 +1215,14 @@ k_hop_expand_ws(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 // ------------------------------------------------------------------------------------------
 constexpr int kTcRows = 128;
 constexpr int kTcChunk = 64;                    // columns per epilogue item = two 32-column TMA boxes
-constexpr int kTcSlots = 4;                     // ring slots per epilogue warp
+template <int R> __host__ __device__ constexpr int tc_slots() { return R <= 16 ? 4 : 3; }   // ring slots per epilogue warp (what fits next to W and H)
 constexpr int kTcQ = 8;                         // entries of the per-CTA tile queue
 constexpr int kTcBoxBytes = 32 * 32 * 4;        // one box: 32 rows x 128 bytes, SWIZZLE_128B (1 KB atoms)
 constexpr int kTcSlotBytes = 2 * kTcBoxBytes;
 
 template <int R>
 constexpr size_t hop_expand_tc_smem(int d) {
-    return (size_t)2 * R * d * 4 + (size_t)4 * R * kTcRows * 4 + (size_t)4 * kTcSlots * kTcSlotBytes + (size_t)d * 4 + 64 * 8 + 64 + 1024;
+    return (size_t)2 * R * d * 4 + (size_t)4 * R * kTcRows * 4 + (size_t)4 * tc_slots<R>() * kTcSlotBytes + (size_t)d * 4 + 64 * 8 + 64 + 1024;
 }
 
 // 2D tiled bulk copies through a tensor map (box = 32 rows x 32 fp32 columns, 128-byte swizzle): one instruction
@@ -1261,11 +1261,13 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 const float* __restrict__ resid, int64_t ldr, const float* __restrict__ scalar,
                 int alpha_is_scalar, int use_resid, float* __restrict__ Hout, float* __restrict__ Out, int64_t ldo,
                 int n, int d, const int* __restrict__ hubitem, const float* __restrict__ hub_part,
-                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, int* sched) {
+                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, int* sched,
+                int pregathered) {
 #ifdef GCA_WS_DEBUG
     const long long ws_entry = clock64();
 #endif
     constexpr int LPG = R / 4, GPW = 32 / LPG;
+    constexpr int kTcSlots = tc_slots<R>();
     constexpr int SCA = (kTcRows >> 3) * 128;          // bytes between 4-column K chunks of the H tile
     constexpr int kHPart = R * kTcRows * 4;            // one of {hi, lo} of one H buffer
     extern __shared__ uint8_t smem_unaligned[];
@@ -1365,7 +1367,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
         struct Meta { int beg, end; float dis; };
         auto meta_load = [&](int tile, int ps) {
             Meta m{0, 0, 0.f};
-            if (tile >= 0) {
+            if (tile >= 0 && !pregathered) {
                 const int row = row_in(tile, ps);
                 if (row < n) { m.beg = __ldg(rowptr + row); m.end = __ldg(rowptr + row + 1); m.dis = __ldg(dis + row); }
             }
@@ -1376,11 +1378,22 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j[u] = (fast && m.beg + u < m.end) ? __ldg(colidx + m.beg + u) : -1;
         };
+        // pregathered = 1 (second half of a split K3): H is already in global memory, the warps only stage their rows
+        auto hrow_load = [&](int tile, int ps) {
+            float4 h_ = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pregathered && tile >= 0) {
+                const int row = row_in(tile, ps);
+                if (row < n) h_ = ldg4(Hout + (size_t)row * R + sub * 4);
+            }
+            return h_;
+        };
+        float4 hp0 = hrow_load(tk, 0), hp1 = hrow_load(tk, 1);
         Meta m0 = meta_load(tk, 0), m1 = meta_load(tk, 1);
         int j0[kPre], j1[kPre];
         idx_load(m0, j0);
         for (int s_ = 0; tk >= 0; ++s_) {
             const int k = s_ / PASSES, ps = s_ - k * PASSES, b = k & 1;
+            const float4 hp2 = ps + 2 < PASSES ? hrow_load(tk, ps + 2) : hrow_load(tk1, ps + 2 - PASSES);
             // step s+2: pass ps+2 of this tile, or pass ps+2-PASSES of the next one
             const Meta m2 = ps + 2 < PASSES ? meta_load(tk, ps + 2) : meta_load(tk1, ps + 2 - PASSES);
             idx_load(m1, j1);
@@ -1415,7 +1428,9 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 if (grp == g_) acc = part;
             }
             float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
+            if (pregathered) {
+                h = hp0;
+            } else if (valid) {
                 h = f4_scale(acc, m0.dis);
                 *reinterpret_cast<float4*>(Hout + (size_t)row * R + sub * 4) = h;
             }
@@ -1434,6 +1449,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
                 if (lane == 0) tc::mbar_arrive(hfull(b));
             }
             m0 = m1; m1 = m2;
+            hp0 = hp1; hp1 = hp2;
 #pragma unroll
             for (int u = 0; u < kPre; ++u) j0[u] = j1[u];
             if (ps == PASSES - 1) { tk = tk1; tk1 = tk >= 0 ? get_tile(k + 2) : -1; }
@@ -2241,11 +2257,20 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
         if (tc_enabled()) {
             static const int use_ws = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && e[0] == 'm') ? 0 : 1; }();
             const size_t smem_ws = sizeof(uint32_t) * ((size_t)2 * R * (d + 1) + (size_t)4 * kTileRows * (R + 4));
+            // When the gathered operand is far larger than L2 the neighbour rows come from HBM and the 8 gather warps of
+            // the fused kernels cannot keep enough of them in flight: run the hop as its own high-occupancy kernel
+            // (k_hop, plain mode: 64 warps per SM) and let the fused kernel only expand the H it left in global memory.
+            static const long long split_bytes = [] { const char* e = getenv("GCA_SPLIT_MB"); return (e ? atoll(e) : 160LL) << 20; }();
+            const bool fused_ok = Out && d <= 256 && n >= 4 * kTcRows;
+            const int pregathered = fused_ok && (long long)c.n_full * R * 4 > split_bytes ? 1 : 0;
+            if (pregathered)
+                GCA_TRY((launch_hop<R, false>(c, F, nullptr, GCA_ACT_NONE, nullptr, nullptr, Hout, nullptr, nullptr, nullptr, n, st, 1,
+                                              W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd")));
             // tcgen05 + bulk-copy variant (GCA_HOP_EXPAND=w falls back to the mma.sync warp-specialised kernel)
             static const int no_tc = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && (e[0] == 'w' || e[0] == 'r' || e[0] == 'm')) ? 1 : 0; }();
-            if constexpr (R == 16) {
-                if (!no_tc && Out && d <= 256 && (d % kTcChunk) == 0 && n >= 4 * kTcRows && (ldo % 4) == 0 &&
-                    (reinterpret_cast<uintptr_t>(Out) % 16) == 0 &&
+            {
+                if (!no_tc && fused_ok && (d % kTcChunk) == 0 && (ldo % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(Out) % 16) == 0 && hop_expand_tc_smem<R>(d) <= 227 * 1024 &&
                     (!use_resid || (resid && (ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) % 16) == 0))) {
                     const size_t smem_tc = hop_expand_tc_smem<R>(d);
                     GCA_TRY(set_smem(k_hop_expand_tc<R, W_IS_DR>, smem_tc));
@@ -2260,20 +2285,12 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                     ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
                     GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
                                         resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y,
-                                        tc_dynamic ? c.sched : nullptr));
+                                        tc_dynamic ? c.sched : nullptr, pregathered));
                     GCA_LAUNCH_OK();
                     return GCA_OK;
                 }
             }
-            if (use_ws && Out && d <= 256 && n >= 4 * kTileRows && smem_ws <= 200 * 1024) {
-                // When the gathered operand is far larger than L2 the neighbour rows come from HBM and the 8 gather warps
-                // of the fused kernel cannot keep enough of them in flight: run the hop as its own high-occupancy kernel
-                // (k_hop, plain mode: 64 warps per SM) and let the fused kernel only expand the H it left in global memory.
-                static const long long split_bytes = [] { const char* e = getenv("GCA_SPLIT_MB"); return (e ? atoll(e) : 160LL) << 20; }();
-                const int pregathered = (long long)c.n_full * R * 4 > split_bytes ? 1 : 0;
-                if (pregathered)
-                    GCA_TRY((launch_hop<R, false>(c, F, nullptr, GCA_ACT_NONE, nullptr, nullptr, Hout, nullptr, nullptr, nullptr, n, st, 1,
-                                                  W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd")));
+            if (use_ws && fused_ok && smem_ws <= 200 * 1024) {
                 const int ntiles_w = (n + kTileRows - 1) / kTileRows;
                 const int grid_w = ntiles_w < num_sms() ? ntiles_w : num_sms();
                 // residual through bulk copies when it fits next to W and the H tiles (GCA_HOP_EXPAND=r: registers)
