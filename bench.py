@@ -82,6 +82,9 @@ def algorithmic_bytes(n, e_prime, d, r):
         "hop_expand_bwd": 2 * nr + idx + dis + 2 * nd,  # gH1' -> gP ; gY -> gX
         "wgrad_down": 2 * nd + nr,                    # X, gY(dot), gP -> gWd partials
         "finalize": 0,
+        # split K3 (operand >> L2, e.g. products-shaped): plain hop kernel + expand-only kernel
+        "hop_plain_fwd": 2 * nr + idx + dis, "hop_plain_bwd": 2 * nr + idx + dis,
+        "expand_fwd": nr + 2 * nd, "expand_bwd": nr + 2 * nd,
     }
     total = 28 * n * d + 52 * n * r + 16 * e_prime + 32 * n
     return per, total

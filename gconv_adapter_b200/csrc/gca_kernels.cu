@@ -2265,7 +2265,8 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
             const int pregathered = fused_ok && (long long)c.n_full * R * 4 > split_bytes ? 1 : 0;
             if (pregathered)
                 GCA_TRY((launch_hop<R, false>(c, F, nullptr, GCA_ACT_NONE, nullptr, nullptr, Hout, nullptr, nullptr, nullptr, n, st, 1,
-                                              W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd")));
+                                              W_IS_DR ? "hop_plain_fwd" : "hop_plain_bwd")));
+            const char* prof_k3 = pregathered ? (W_IS_DR ? "expand_fwd" : "expand_bwd") : (W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd");
             // tcgen05 + bulk-copy variant (GCA_HOP_EXPAND=w falls back to the mma.sync warp-specialised kernel)
             static const int no_tc = [] { const char* e = getenv("GCA_HOP_EXPAND"); return (e && (e[0] == 'w' || e[0] == 'r' || e[0] == 'm')) ? 1 : 0; }();
             {
@@ -2282,7 +2283,7 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                     CUtensorMap tm_x, tm_y;
                     if (!make_box_map(&tm_y, Out, n, d, ldo) || !make_box_map(&tm_x, use_resid ? resid : Out, n, d, use_resid ? ldr : ldo))
                         return GCA_ERR_CUDA;
-                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                    ProfScope ps(prof_k3, st);
                     GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
                                         resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y,
                                         tc_dynamic ? c.sched : nullptr, pregathered));
@@ -2298,7 +2299,7 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                 const size_t smem_xt = smem_ws + 32 + sizeof(float) * (size_t)2 * kTileRows * (d + 16) + 16;
                 const bool xt = !no_xt && use_resid && resid && (ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) % 16) == 0 &&
                                 smem_xt <= 227 * 1024;
-                ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                ProfScope ps(prof_k3, st);
                 if (xt) {
                     GCA_TRY(set_smem(k_hop_expand_ws<R, W_IS_DR, true>, smem_xt));
                     GCA_CUDA(launch_pdl(k_hop_expand_ws<R, W_IS_DR, true>, dim3(grid_w), dim3(512), smem_xt, st, rowptr, colidx, dis, F, W, bias,
