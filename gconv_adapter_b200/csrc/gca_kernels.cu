@@ -2167,9 +2167,16 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
         // two tensor-core variants: tcgen05 (UMMA + TMEM, shared-memory operand pipeline) and register-level
         // mma.sync (operands straight from global memory).  GCA_PROJECT=tcgen05|mma picks one; default = mma,
         // which measured faster at these skinny shapes (N = r <= 32 makes the tcgen05 path shared-memory bound).
-        static const int prefer_tcgen05 = [] { const char* e = getenv("GCA_PROJECT"); return (e && e[0] == 't') ? 1 : 0; }();
+        // (r = 32 doubles the 3xTF32 mma.sync work to ~0.86 ms of tensor pipe at products size; there the tcgen05 kernel
+        //  wins: 0.69 vs 0.84 ms)
+        static const int proj_env = [] { const char* e = getenv("GCA_PROJECT"); return !e ? 0 : (e[0] == 't' ? 1 : (e[0] == 'm' ? 2 : 0)); }();
+        const int prefer_tcgen05 = proj_env == 1 || (proj_env == 0 && R == 32);
+        if (prefer_tcgen05) {
+            const int st_first = launch_project_tc(R, W_IS_RD, A, lda, W, rowscale, scalar, out, n, d, st);
+            if (st_first != GCA_ERR_UNSUPPORTED) return st_first;
+        }
         if constexpr (R == 16 || R == 32) {
-            if (!prefer_tcgen05 && d % 16 == 0) {
+            if (d % 16 == 0) {
                 const size_t smem_m = sizeof(uint4) * (size_t)(d / 16) * 2 * 4 * (R / 8) * 8;
                 if (smem_m <= 100 * 1024) {
                     GCA_TRY(set_smem(k_project_mma<R, W_IS_RD>, smem_m));
@@ -2185,8 +2192,10 @@ int launch_project(const float* A, int64_t lda, const float* W, const float* row
                 }
             }
         }
-        const int st_tc = launch_project_tc(R, W_IS_RD, A, lda, W, rowscale, scalar, out, n, d, st);
-        if (st_tc != GCA_ERR_UNSUPPORTED) return st_tc;
+        if (!prefer_tcgen05) {
+            const int st_tc = launch_project_tc(R, W_IS_RD, A, lda, W, rowscale, scalar, out, n, d, st);
+            if (st_tc != GCA_ERR_UNSUPPORTED) return st_tc;
+        }
     }
     constexpr int TILE = 32 * (64 / R);
     const size_t smem = sizeof(float) * (size_t)(d / 4) * (4 * R + 4);
