@@ -2244,7 +2244,14 @@ int launch_hop(const Csr& c, const float* F, const float* bias, int act,
     GCA_TRY(launch_hub_partials<R>(c, F, st));
     const int* rowptr = c.rowptr; const int* colidx = c.colidx; const float* dis = c.dis;
     int grid = (n + 8 * GPW - 1) / (8 * GPW);
-    const int cap = BWD ? (kMaxPartsBd < 8 * num_sms() ? kMaxPartsBd : 8 * num_sms()) : 8 * num_sms();
+    // one resident wave: the warps loop over their row batches; a second, partially filled wave of CTAs only adds a tail
+    static const int per_sm = [] {
+        const char* e = getenv("GCA_HOP_CTAS");
+        int v = e ? atoi(e) : 0;
+        if (v <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_hop<R, BWD>, 256, 0) != cudaSuccess) v = 0;
+        return v > 0 && v <= 16 ? v : 8;
+    }();
+    const int cap = BWD ? (kMaxPartsBd < per_sm * num_sms() ? kMaxPartsBd : per_sm * num_sms()) : per_sm * num_sms();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     {
