@@ -1,16 +1,28 @@
-// Forward / backward kernels of the GConv-Adapter hot path (sm_100a, fp32).
+// Forward / backward kernels of the GConv-Adapter hot path (sm_100a, fp32).  Index of this file, default variant first:
 //
-//   K1 k_project      skinny projection  [n,d] x [d,R] -> [n,R]      (conv_down.lin ; gH2 = gY Wu)
-//   K2 k_hop          r-wide gather-SpMM (+bias, act, or act')        (conv_down.propagate and its transpose)
-//   K3 k_hop_expand   r-wide gather-SpMM on a 64-row tile staged in shared memory, fused with the
-//                     [64,R] x [R,d] expansion, bias, residual and scalar epilogue
-//                     (conv_up + skip + scalar ; gP -> gX)
-//   K4 k_wgrad        weight-gradient reduction  G[R,d] = H^T A  with per-CTA partials (no atomics)
-//   K6 k_finalize     deterministic second-stage reduction of all partials
+//   K1 projection  [n,d] x [d,R] -> [n,R]                  (conv_down.lin ; gH2' = gY Wu)
+//        k_project_mma      3xTF32 mma.sync, fragments straight from global, dynamic m-tiles        (r = 16)
+//        tc::k_project_tc   tcgen05 / TMEM, in gca_tc_project.cu                                    (r = 32)
+//        k_project          FFMA, register-tiled                                                    (other shapes)
+//   K2 k_hop        r-wide gather-SpMM (+bias, act | act' + bias-gradient partials | plain hop of a split K3)
+//                   (conv_down.propagate and its transpose); k_hub_partials: work items of hub rows (degree > 512)
+//   K3 hop + expand r-wide gather-SpMM of a row tile fused with the [rows,R] x [R,d] expansion, bias, residual, scalar
+//                   (conv_up + skip + scalar ; gP -> gX)
+//        k_hop_expand_tc    tcgen05 / TMEM accumulator, tensor-map TMA in and out, 128-row tiles (r = 16 / 32, d % 64 == 0)
+//        k_hop_expand_ws    warp-specialised mma.sync, pipelined gather warps, optional bulk-copy residual
+//        k_hop_expand_mma   mma.sync, one kernel per 64-row tile ; k_hop_expand: FFMA
+//   K4 weight gradient  G[R,d] = H^T A  (+ column sums, <A,B>) with per-CTA partials, no atomics
+//        k_wgrad_stream     mma.sync, one contiguous row range per CTA, H fragments as LDS.128 quads
+//        k_wgrad_mma        older 128-row-tile variant (GCA_WGRAD=tile) ; k_wgrad: FFMA
+//        k_bwd_up_fused     project_bwd + wgrad_up in one launch (opt-in, GCA_BWD_UP=fused)
+//   K6 k_finalize   deterministic second-stage reduction of all partials + gscalar
+//   k_propagate     d-wide normalised SpMM over the same handle (backbone propagation, gca_propagate)
+//   host side       launch_* helpers (variant selection, environment switches), extern "C" entry points of gca.h
 //
 // Reference semantics: /root/reference/src/finetune/gconv_adapter.py:92-106 (see include/gca.h).
-// Sparse rows are processed by lane groups (R/4 lanes x 128-bit loads per neighbour row); rows
-// longer than kLongRow are swept by the whole warp.  All reductions have a fixed order.
+// Sparse rows are processed by lane groups (R/4 lanes x 128-bit loads per neighbour row); rows longer than kLongRow
+// are swept by the whole warp, rows longer than kHubDeg are pre-reduced per work item.  All reductions have a fixed
+// order.  -DGCA_WS_DEBUG adds per-role cycle counters to the K3 kernels (profiles/ws_debug_timing.py).
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
