@@ -2309,14 +2309,15 @@ int launch_hop_expand(const Csr& c, const float* F, const float* W,
                     // static round-robin sequence (81 vs 76 us: the last tiles are handed out one by one), so it is off
                     static const bool tc_dynamic = [] { const char* e = getenv("GCA_TC_DYNAMIC"); return e && e[0] == '1'; }();
                     CUtensorMap tm_x, tm_y;
-                    if (!make_box_map(&tm_y, Out, n, d, ldo) || !make_box_map(&tm_x, use_resid ? resid : Out, n, d, use_resid ? ldr : ldo))
-                        return GCA_ERR_CUDA;
-                    ProfScope ps(prof_k3, st);
-                    GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
-                                        resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y,
-                                        tc_dynamic ? c.sched : nullptr, pregathered));
-                    GCA_LAUNCH_OK();
-                    return GCA_OK;
+                    // (a driver without cuTensorMapEncodeTiled, or a tensor it refuses, leaves the mma.sync kernels below)
+                    if (make_box_map(&tm_y, Out, n, d, ldo) && make_box_map(&tm_x, use_resid ? resid : Out, n, d, use_resid ? ldr : ldo)) {
+                        ProfScope ps(prof_k3, st);
+                        GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
+                                            resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y,
+                                            tc_dynamic ? c.sched : nullptr, pregathered));
+                        GCA_LAUNCH_OK();
+                        return GCA_OK;
+                    }
                 }
             }
             if (use_ws && fused_ok && smem_ws <= 200 * 1024) {
