@@ -12,8 +12,12 @@ import threading
 
 log = logging.getLogger("gconv_adapter_b200")
 
-# GCA_LIB_PATH selects an alternative build of the same library (profiling experiments only).
-LIB_PATH = os.environ.get("GCA_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgca.so")
+from . import build as _build
+
+# The library file name carries the hash of the sources it was built from (gconv_adapter_b200/build.py), so a binary
+# of older sources is never loaded.  GCA_LIB_PATH selects an alternative build (profiling experiments only).
+LIB_PATH = os.environ.get("GCA_LIB_PATH") or _build.lib_path()
+ABI_VERSION = 2
 
 GCA_OK = 0
 GCA_ERR_INDEX_RANGE = -4
@@ -41,20 +45,21 @@ SIGNATURES = {
     "gca_graph_destroy": (None, [_f]),
     "gca_graph_get_view": (C.c_int, [_f, C.POINTER(GraphView)]),
     "gca_graph_edge_coef": (C.c_int, [_f, _f, _f]),
+    "gca_hub_scratch_bytes": (_sz, [_f]),
     "gca_propagate": (C.c_int, [_f, C.c_int, _f, _i64, _f, _i64, _i32, _f]),
     "gca_fwd_project": (C.c_int, [_f, _f, _i64, _f, _f, _i32, _i32, _f]),
-    "gca_fwd_hop1": (C.c_int, [_f, _f, _f, C.c_int, _f, _f, _i32, _f]),
-    "gca_fwd_hop2_up": (C.c_int, [_f, _f, _f, _i64, _f, _f, _f, C.c_int, _f, _f, _i64, _i32, _i32, _f]),
+    "gca_fwd_hop1": (C.c_int, [_f, _f, _f, C.c_int, _f, _f, _f, _i32, _f]),
+    "gca_fwd_hop2_up": (C.c_int, [_f, _f, _f, _i64, _f, _f, _f, C.c_int, _f, _f, _i64, _f, _i32, _i32, _f]),
     "gca_bwd_scratch_bytes": (_sz, [_i32, _i32]),
     "gca_bwd_up": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f]),
     "gca_bwd_up_project": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _i32, _i32, _f]),
     "gca_bwd_up_wgrad": (C.c_int, [_f, _f, _i64, _f, _f, _i32, _i32, _f]),
-    "gca_bwd_hop2": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _i32, _f]),
-    "gca_bwd_hop1_down": (C.c_int, [_f, _f, _f, _i64, _f, _i64, _f, _f, C.c_int, _f, _f, _i64, _f, _i32, _i32, _f]),
+    "gca_bwd_hop2": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _f, _i32, _f]),
+    "gca_bwd_hop1_down": (C.c_int, [_f, _f, _f, _i64, _f, _i64, _f, _f, C.c_int, _f, _f, _i64, _f, _f, _i32, _i32, _f]),
     "gca_bwd_finalize": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _f, _f, _f, _i32, _i32, _f]),
-    "gca_forward_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "gca_forward_workspace_bytes": (_sz, [_f, _i32, _i32]),
     "gca_forward": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _f, C.c_int, C.c_int, _f, _f, _f, _f, _f, _i64, _i32, _i32, _f]),
-    "gca_backward_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "gca_backward_workspace_bytes": (_sz, [_f, _i32, _i32]),
     "gca_backward": (C.c_int, [_f, _f, _i64, _f, _i64, _f, _f, _f, _f, _f, _f, _f, C.c_int, C.c_int, _f,
                                _f, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f]),
     "gca_launch_count": (_i64, []),
@@ -75,14 +80,14 @@ def load():
         if _lib is None:
             if not os.path.isfile(LIB_PATH):
                 raise RuntimeError(
-                    f"gconv_adapter_b200: CUDA library not built ({LIB_PATH} missing). "
+                    f"gconv_adapter_b200: CUDA library not built for these sources ({LIB_PATH} missing). "
                     "Run `python -m gconv_adapter_b200.build` (needs nvcc); there is no CPU fallback.")
             lib = C.CDLL(LIB_PATH)
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.gca_abi_version() != 1:
+            if lib.gca_abi_version() != ABI_VERSION:
                 raise RuntimeError("gconv_adapter_b200: libgca.so ABI version mismatch; rebuild it")
             _lib = lib
     return _lib

@@ -19,15 +19,15 @@ struct gca_graph {
     float* dis;
     int32_t* cnt;      // [n] counters / fill cursors (forward CSR)
     int32_t* cnt_t;    // [n] counters / fill cursors (transposed CSR)
-    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t, [3] hub items, [4] hub items (transpose),
-                       // [5] dynamic tile counter and [6] finished-CTA counter of the kernel currently running on this handle
+    int32_t* flags;    // [0] index-range error, [1] nnz, [2] nnz_t, [3] hub items, [4] hub items (transpose); written by the
+                       // build only: the handle carries NO per-launch mutable state (re-entrant per (handle, stream))
     // Hub rows (degree > kHubDeg) are cut into work items of kHubChunk neighbours (see gca_graph.cu / k_hub_partials)
     int32_t* hubitem;      // [n]  first item of a hub row, -1 otherwise          (forward CSR)
     int32_t* hubitem_t;    // [n]                                                 (transposed CSR)
     int32_t* item_row;     // [hub_cap] local row of an item
     int32_t* item_row_t;
-    float* hub_part;       // [hub_cap][64] partial sums of the items (scratch, one stream at a time per handle)
-    int64_t hub_cap;
+    int64_t hub_cap;       // capacity of the item lists; the items' partial sums live in per-call scratch of
+                           // hub_cap * 64 floats supplied by the caller (gca_hub_scratch_bytes)
     int32_t nitems, nitems_t;   // host copies after gca_graph_validate; -1 = unknown
 };
 

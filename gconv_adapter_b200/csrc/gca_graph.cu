@@ -302,7 +302,7 @@ __global__ void k0_edge_coef(const int* __restrict__ rowptr, const int* __restri
 }
 
 struct Layout {
-    size_t rowptr, rowptr_t, colidx, colidx_t, dis, hubitem, hubitem_t, item_row, item_row_t, hub_part, cnt, cnt_t, flags, total;
+    size_t rowptr, rowptr_t, colidx, colidx_t, dis, hubitem, hubitem_t, item_row, item_row_t, cnt, cnt_t, flags, total;
     size_t hub_cap;
 };
 Layout make_layout(int64_t E, int32_t n) {
@@ -320,7 +320,6 @@ Layout make_layout(int64_t E, int32_t n) {
     L.hubitem_t = off;  off += align_up(sizeof(int32_t) * ((size_t)n + 1));
     L.item_row = off;   off += align_up(sizeof(int32_t) * L.hub_cap);
     L.item_row_t = off; off += align_up(sizeof(int32_t) * L.hub_cap);
-    L.hub_part = off;   off += align_up(sizeof(float) * L.hub_cap * 64);
     L.cnt = off;      off += align_up(sizeof(int32_t) * ((size_t)n + 1));
     L.cnt_t = off;    off += align_up(sizeof(int32_t) * ((size_t)n + 1));
     L.flags = off;    off += align_up(sizeof(int32_t) * 8);
@@ -366,7 +365,6 @@ extern "C" int gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E
     g->hubitem_t = reinterpret_cast<int32_t*>(base + L.hubitem_t);
     g->item_row = reinterpret_cast<int32_t*>(base + L.item_row);
     g->item_row_t = reinterpret_cast<int32_t*>(base + L.item_row_t);
-    g->hub_part = reinterpret_cast<float*>(base + L.hub_part);
     g->hub_cap = (int64_t)L.hub_cap;
     g->nitems = g->nitems_t = -1;
     g->cnt = reinterpret_cast<int32_t*>(base + L.cnt);

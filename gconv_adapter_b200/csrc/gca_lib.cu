@@ -6,9 +6,13 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
+#include <cuda.h>
+
 #include "gca_common.cuh"
+#include "gca_host.cuh"
 
 namespace gca {
 
@@ -16,34 +20,97 @@ static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
-    static int cached = 0;
-    if (cached > 0) return cached;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-        sms = 148;   // B200
-    cached = sms;
-    return cached;
+    // cached per device: one process may drive several GPUs (torch.cuda.set_device between calls)
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;   // B200
+    cache[dev] = sms;
+    return sms;
 }
 
-// GCA_DISABLE_TC=1 forces the CUDA-core kernels (A/B runs, debugging).
-bool tc_enabled() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("GCA_DISABLE_TC");
-        cached = (e && e[0] == '1') ? 0 : 1;
-    }
-    return cached == 1;
+static bool env_flag(const char* name) {
+    const char* e = getenv(name);
+    return e && e[0] == '1';
+}
+// Run-time switches (diagnostics / A-B runs; every one of them is exercised by tests/test_gpu_switches.py):
+//   GCA_DISABLE_TC=1      CUDA-core (FFMA) kernels everywhere
+//   GCA_DISABLE_STREAM=1  register-fed mma.sync projection / weight gradient instead of the TMA-fed family
+//   GCA_DISABLE_TMA=1     behave as if the driver refused every tensor map (kernels that need none take over)
+//   GCA_DISABLE_PDL=1     every kernel fully serialised (no programmatic dependent launch)
+//   GCA_SPLIT_MB=<n>      gathered operand above n MB: K3 = plain hop + expand-only (default 160)
+bool tc_enabled() { static const bool on = !env_flag("GCA_DISABLE_TC"); return on; }
+bool stream_enabled() { static const bool on = !env_flag("GCA_DISABLE_STREAM"); return on; }
+bool pdl_enabled() { static const bool on = !env_flag("GCA_DISABLE_PDL"); return on; }
+long long split_bytes() {
+    static const long long v = [] { const char* e = getenv("GCA_SPLIT_MB"); return (e ? atoll(e) : 160LL) << 20; }();
+    return v;
 }
 
-// GCA_DISABLE_PDL=1 launches every kernel fully serialised (A/B runs).
-bool pdl_enabled() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("GCA_DISABLE_PDL");
-        cached = (e && e[0] == '1') ? 0 : 1;
+int set_smem_impl(const void* kernel, size_t bytes, bool has_static_smem) {
+    if (bytes <= 48 * 1024 && !has_static_smem) return GCA_OK;   // static + dynamic > 48 KB needs the opt-in too
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    GCA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair(dev, kernel);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return GCA_OK;
+    GCA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
+    return GCA_OK;
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
+bool get_box_map(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ld, int box_cols, int box_rows, bool swizzle) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn enc = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    static const bool disabled = env_flag("GCA_DISABLE_TMA");
+    if (!enc || disabled) return false;
+    // A map depends only on (address, shape, pitch, box), not on the data: the training loop presents the same few
+    // tensors every step, so a small per-thread cache removes the host-side encode from the launch path.
+    struct Key { const float* base; int rows, cols; int64_t ld; int bc, br, sw; };
+    struct Entry { Key k; CUtensorMap tm; uint64_t stamp; };
+    constexpr int kCap = 32;
+    static thread_local Entry cache[kCap];
+    static thread_local int used = 0;
+    static thread_local uint64_t clock_ = 0;
+    const Key k{base, rows, cols, ld, box_cols, box_rows, swizzle ? 1 : 0};
+    int victim = 0;
+    for (int i = 0; i < used; ++i) {
+        const Key& c = cache[i].k;
+        if (c.base == k.base && c.rows == k.rows && c.cols == k.cols && c.ld == k.ld && c.bc == k.bc && c.br == k.br && c.sw == k.sw) {
+            cache[i].stamp = ++clock_;
+            *tm = cache[i].tm;
+            return true;
+        }
+        if (cache[i].stamp < cache[victim].stamp) victim = i;
     }
-    return cached == 1;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    const int slot = used < kCap ? used++ : victim;
+    cache[slot] = Entry{k, *tm, ++clock_};
+    return true;
 }
 
 struct ProfEntry { const char* name; cudaEvent_t a, b; };

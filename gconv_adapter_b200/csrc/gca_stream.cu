@@ -1,0 +1,398 @@
+// TMA-fed dense streaming family: every dense pass over a d-wide tensor of the adapter in ONE kernel template.
+//
+//   project_fwd   P'   = dis * (X Wd^T)                                   PROJ            (conv_down.lin)
+//   bwd_up        gH2' = dis * s * (gY Wu)  AND  gWu/gbu partials         PROJ + WGRAD    gY crosses HBM ONCE
+//   wgrad_down    gWd partials = gP^T X  AND  <gY, X>                     WGRAD + DOT
+//
+// Why: the register-fed mma.sync kernels (gca_project.cu, gca_wgrad.cu) reach 47-49 % of the HBM peak at 24 % warps
+// active - every LDG of a warp shares one scoreboard, so a warp never overlaps its own loads with its tensor-core work
+// (profiles/README.md section 2b) - and the backward read gY once for the projection and once more for the weight
+// gradient.  Here the copy engine streams [32 rows x d] tiles into a shared-memory ring (tensor-map boxes of
+// 32 x 32 fp32, SWIZZLE_128B, mbarrier hand-over) and warp-specialised consumers read every tile from shared memory:
+//
+//   warp 0        producer: one thread issues the boxes of tile k + stages - 1 as soon as all consumers released the stage
+//   warps 1-8     projection (if PROJ): warp w owns the 32-column box w of every tile (W fragments for those 32 k's
+//                 live in registers, split into tf32 hi / lo once), multiplies both 16-row m-tiles of the tile and
+//                 leaves a [32, R] partial in shared memory; after a named barrier four of the eight warps
+//                 (alternating) add the eight partials in box order, scale and store the rows.
+//   next 8 warps  weight gradient (if WGRAD): warp w owns the same box w as the N dimension (32 columns = 4 n-tiles),
+//                 K = the 32 rows of the tile (4 k-steps), M = R.  The H tile [32, R] arrives through its own
+//                 tensor map in the same stage.  Accumulators stay in registers for the whole kernel (folded into a
+//                 running fp32 sum every 4 tiles: the tensor core's accumulator truncates) -> ONE partial per CTA.
+//
+// Fragment reads are bank-conflict free by construction (g = lane >> 2, t = lane & 3):
+//   projection A-fragment: LDS.128 of chunk 4*kb2 + t of rows pg(g) and pg(g) + 8 with pg(g) = (g >> 1) + 4 (g & 1):
+//       a quarter warp (g in {2q, 2q+1}) touches rows q and q + 4, whose swizzle XORs differ in bit 2.
+//       One float4 feeds two k-steps through the K permutation  k-step s: k = t -> column 4t + 2s, k = t + 4 -> 4t + 2s + 1.
+//   weight-gradient B-fragment: LDS.128 of chunk g of rows 8 ks + {0,3,4,7}[t] (b0) and 8 ks + {1,2,5,6}[t] (b1); the
+//       float4 feeds the four n-tiles through the column permutation  col = 32 w + 4 n + j  (n-tile j).
+// 3xTF32 as everywhere: x = hi + lo, A B ~= A_hi B_hi + A_lo B_hi + A_hi B_lo (error ~2^-21 per product).
+//
+// Reference semantics: the two Linear layers of /root/reference/src/finetune/gconv_adapter.py:92 and their autograd.
+#include "gca_common.cuh"
+#include "gca_device.cuh"
+#include "gca_host.cuh"
+
+namespace gca {
+namespace {
+
+constexpr int kSRows = 32;                 // rows per tile
+constexpr int kSBox = 32 * kSRows * 4;     // one 32-column box of a tile: 4 KB, SWIZZLE_128B
+constexpr int kSWarps = 8;                 // consumer warps per role = column boxes of a 256-wide tile
+constexpr int kSFold = 4;                  // tiles between two folds of the tensor-core accumulators
+
+struct StreamParams {
+    const float* W; const float* rowscale; const float* scalar; float* out;
+    float* partG; float* partCol; float* partDot; int* header; int slot;
+    int n, d, nb, stages;
+    uint32_t stage_bytes, b_off, h_off, tx_bytes, red_off, bar_off;
+};
+
+// byte offset of the 16-byte chunk `chunk` of row `row` inside a box of 128-byte rows with the 128-byte swizzle
+__device__ __forceinline__ uint32_t box_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+__device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD>
+__global__ void __launch_bounds__(32 * (1 + (PROJ ? kSWarps : 0) + (WGRAD ? kSWarps : 0)), 1)
+k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmH, const StreamParams p) {
+    constexpr int NT = R / 8, MT = R / 16;
+    constexpr int kConsumers = (PROJ ? kSWarps : 0) + (WGRAD ? kSWarps : 0);
+    extern __shared__ uint8_t smem_unaligned[];
+    uint8_t* smem = smem_unaligned + ((1024u - (smem_addr(smem_unaligned) & 1023u)) & 1023u);
+    const uint32_t bar0 = smem_addr(smem + p.bar_off);
+    auto full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto empty = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), kConsumers); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // what precedes these kernels on the stream is either not ours (an optimizer step may just have written W) or
+    // produced the H operand: wait before the first read of anything
+    pdl_wait();
+    pdl_trigger();
+
+    // contiguous tile ranges: CTA b takes q (+1) consecutive tiles, so its partial covers one row range
+    const int ntiles = (p.n + kSRows - 1) / kSRows;
+    const int q = ntiles / (int)gridDim.x, rem = ntiles % (int)gridDim.x;
+    const int bid = blockIdx.x;
+    const int t0 = bid * q + min(bid, rem);
+    const int my_tiles = q + (bid < rem ? 1 : 0);
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int s = 0, use = 0;
+            for (int k = 0; k < my_tiles; ++k) {
+                if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
+                const int row0 = (t0 + k) * kSRows;
+                const uint32_t dst = smem_addr(smem + (size_t)s * p.stage_bytes);
+                mbar_arrive_expect_tx(full(s), p.tx_bytes);
+                for (int b = 0; b < p.nb; ++b) tma_load_box(dst + (uint32_t)(b * kSBox), &tmA, b * 32, row0, full(s), pol);
+                if (DOT)
+                    for (int b = 0; b < p.nb; ++b) tma_load_box(dst + p.b_off + (uint32_t)(b * kSBox), &tmB, b * 32, row0, full(s), pol);
+                if (WGRAD) tma_load_box_nohint(dst + p.h_off, &tmH, 0, row0, full(s));
+                if (++s == p.stages) { s = 0; ++use; }
+            }
+        }
+        return;
+    }
+    const int cw = warp - 1;
+    const int g = lane >> 2, t = lane & 3;
+
+    if (PROJ && cw < kSWarps) {
+        // ===================== projection warps =====================
+        const int bx = cw;
+        const bool active = bx < p.nb;
+        // W fragments of this warp's 32 k's: wf[ks][nt] = {hi(k0,c), hi(k1,c), lo(k0,c), lo(k1,c)},
+        // k0 = 32 bx + 16 (ks >> 1) + 4 t + 2 (ks & 1), k1 = k0 + 1, c = 8 nt + g
+        uint32_t wf[4][NT][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int k0 = 32 * bx + 16 * (ks >> 1) + 4 * t + 2 * (ks & 1);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int c = nt * 8 + g;
+                float w0 = 0.f, w1 = 0.f;
+                if (active) {
+                    w0 = W_IS_RD ? __ldg(p.W + (size_t)c * p.d + k0) : __ldg(p.W + (size_t)k0 * R + c);
+                    w1 = W_IS_RD ? __ldg(p.W + (size_t)c * p.d + k0 + 1) : __ldg(p.W + (size_t)(k0 + 1) * R + c);
+                }
+                split_tf32(w0, wf[ks][nt][0], wf[ks][nt][2]);
+                split_tf32(w1, wf[ks][nt][1], wf[ks][nt][3]);
+            }
+        }
+        const float sc_s = p.scalar ? __ldg(p.scalar) : 1.f;
+        const int pg = (g >> 1) + 4 * (g & 1);
+        float4* red = reinterpret_cast<float4*>(smem + p.red_off);          // [2][kSWarps][2 NT][32]
+        constexpr int kSlots = 2 * NT * 32;                                  // float4 per partial
+        int s = 0;
+        uint32_t ph = 0;
+        for (int k = 0; k < my_tiles; ++k) {
+            float acc[2][2][NT][4];
+#pragma unroll
+            for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[a_][mt][nt][i] = 0.f;
+            mbar_wait(full(s), ph);
+            if (active) {
+                const uint8_t* box = smem + (size_t)s * p.stage_bytes + bx * kSBox;
+#pragma unroll
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const int r_lo = 16 * mt + pg, r_hi = r_lo + 8;
+                        const float4 x0 = lds4(box + box_off(r_lo, 4 * kb2 + t));
+                        const float4 x1 = lds4(box + box_off(r_hi, 4 * kb2 + t));
+                        const float e0[4] = {x0.x, x0.y, x0.z, x0.w};
+                        const float e1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                        for (int s2 = 0; s2 < 2; ++s2) {
+                            uint32_t ah[4], al[4];
+                            split_tf32(e0[2 * s2], ah[0], al[0]);        // (row g,   k = t)
+                            split_tf32(e1[2 * s2], ah[1], al[1]);        // (row g+8, k = t)
+                            split_tf32(e0[2 * s2 + 1], ah[2], al[2]);    // (row g,   k = t+4)
+                            split_tf32(e1[2 * s2 + 1], ah[3], al[3]);    // (row g+8, k = t+4)
+                            const int ks = kb2 * 2 + s2;
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) {
+                                mma_tf32(acc[0][mt][nt], ah, wf[ks][nt][0], wf[ks][nt][1]);
+                                mma_tf32(acc[1][mt][nt], al, wf[ks][nt][0], wf[ks][nt][1]);
+                                mma_tf32(acc[1][mt][nt], ah, wf[ks][nt][2], wf[ks][nt][3]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(s));                            // this warp is done with the stage
+            float4* mine = red + ((size_t)(k & 1) * kSWarps + bx) * kSlots;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    mine[(mt * NT + nt) * 32 + lane] =
+                        make_float4(acc[0][mt][nt][0] + acc[1][mt][nt][0], acc[0][mt][nt][1] + acc[1][mt][nt][1],
+                                    acc[0][mt][nt][2] + acc[1][mt][nt][2], acc[0][mt][nt][3] + acc[1][mt][nt][3]);
+            named_sync(1, kSWarps * 32);
+            // Two partial buffers: a warp may already be writing tile k+1 into the other one while the reducers of
+            // tile k read this one, and nobody reaches tile k+2 before every reducer of tile k passed barrier k+1.
+            if ((bx >> 2) == (k & 1)) {
+                const float4* rb = red + (size_t)(k & 1) * kSWarps * kSlots;
+                for (int idx = (bx & 3) * 32 + lane; idx < kSlots; idx += 128) {
+                    float4 v = rb[idx];
+#pragma unroll
+                    for (int w = 1; w < kSWarps; ++w) v = f4_add(v, rb[w * kSlots + idx]);   // box order: fixed
+                    const int slot = idx >> 5, ln = idx & 31, g2 = ln >> 2, t2 = ln & 3;
+                    const int mt = slot / NT, nt = slot - mt * NT;
+                    const int row_a = (t0 + k) * kSRows + 16 * mt + (g2 >> 1) + 4 * (g2 & 1), row_b = row_a + 8;
+                    if (row_a < p.n) {
+                        const float sc = (p.rowscale ? __ldg(p.rowscale + row_a) : 1.f) * sc_s;
+                        *reinterpret_cast<float2*>(p.out + (size_t)row_a * R + nt * 8 + 2 * t2) = make_float2(v.x * sc, v.y * sc);
+                    }
+                    if (row_b < p.n) {
+                        const float sc = (p.rowscale ? __ldg(p.rowscale + row_b) : 1.f) * sc_s;
+                        *reinterpret_cast<float2*>(p.out + (size_t)row_b * R + nt * 8 + 2 * t2) = make_float2(v.z * sc, v.w * sc);
+                    }
+                }
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        return;
+    }
+
+    if (WGRAD) {
+        // ===================== weight-gradient warps =====================
+        const int bx = PROJ ? cw - kSWarps : cw;
+        const bool active = bx < p.nb;
+        float acc[MT][4][4], run[MT][4][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[m][j][i] = 0.f; run[m][j][i] = 0.f; }
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dot = 0.f;
+        const int rA = 4 * (t >> 1) + 3 * (t & 1);          // {0, 3, 4, 7}[t]  -> k = t
+        const int rB = 4 * (t >> 1) + 1 + (t & 1);          // {1, 2, 5, 6}[t]  -> k = t + 4
+        auto hload = [&](const uint8_t* ht, int row, int c) -> float {
+            if (R == 32) return *reinterpret_cast<const float*>(ht + box_off(row, c >> 2) + (c & 3) * 4);   // swizzled 128-byte rows
+            return *reinterpret_cast<const float*>(ht + (row * R + c) * 4);
+        };
+        auto fold = [&]() {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { run[m][j][i] += acc[m][j][i]; acc[m][j][i] = 0.f; }
+        };
+        int s = 0;
+        uint32_t ph = 0;
+        for (int k = 0; k < my_tiles; ++k) {
+            mbar_wait(full(s), ph);
+            if (active) {
+                const uint8_t* stg = smem + (size_t)s * p.stage_bytes;
+                const uint8_t* boxA = stg + bx * kSBox;
+                const uint8_t* boxB = stg + p.b_off + bx * kSBox;
+                const uint8_t* ht = stg + p.h_off;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int ra = 8 * ks + rA, rb = 8 * ks + rB;
+                    const float4 va = lds4(boxA + box_off(ra, g)), vb = lds4(boxA + box_off(rb, g));
+                    uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+                    split_tf32(va.x, bh0[0], bl0[0]); split_tf32(va.y, bh0[1], bl0[1]);
+                    split_tf32(va.z, bh0[2], bl0[2]); split_tf32(va.w, bh0[3], bl0[3]);
+                    split_tf32(vb.x, bh1[0], bl1[0]); split_tf32(vb.y, bh1[1], bl1[1]);
+                    split_tf32(vb.z, bh1[2], bl1[2]); split_tf32(vb.w, bh1[3], bl1[3]);
+                    if (DOT) {
+                        const float4 wa = lds4(boxB + box_off(ra, g)), wb = lds4(boxB + box_off(rb, g));
+                        dot = fmaf(va.x, wa.x, fmaf(va.y, wa.y, fmaf(va.z, wa.z, fmaf(va.w, wa.w, dot))));
+                        dot = fmaf(vb.x, wb.x, fmaf(vb.y, wb.y, fmaf(vb.z, wb.z, fmaf(vb.w, wb.w, dot))));
+                    } else {
+                        csum = f4_add(csum, f4_add(va, vb));
+                    }
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        uint32_t ah[4], al[4];
+                        split_tf32(hload(ht, ra, 16 * m + g), ah[0], al[0]);        // (c = g,   k = t)
+                        split_tf32(hload(ht, ra, 16 * m + g + 8), ah[1], al[1]);    // (c = g+8, k = t)
+                        split_tf32(hload(ht, rb, 16 * m + g), ah[2], al[2]);        // (c = g,   k = t+4)
+                        split_tf32(hload(ht, rb, 16 * m + g + 8), ah[3], al[3]);    // (c = g+8, k = t+4)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], ah, bh0[j], bh1[j]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], al, bh0[j], bh1[j]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mma_tf32(acc[m][j], ah, bl0[j], bl1[j]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(s));
+            if ((k % kSFold) == kSFold - 1) fold();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        fold();
+        // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns 32 bx + 8t .. + 7 ----
+        if (active) {
+            float* pgp = p.partG + (size_t)bid * R * p.d;
+            const int oc = 32 * bx + 8 * t;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c = m * 16 + g + 8 * half;
+                    const int i0 = 2 * half;
+                    *reinterpret_cast<float4*>(pgp + (size_t)c * p.d + oc) =
+                        make_float4(run[m][0][i0], run[m][1][i0], run[m][2][i0], run[m][3][i0]);
+                    *reinterpret_cast<float4*>(pgp + (size_t)c * p.d + oc + 4) =
+                        make_float4(run[m][0][i0 + 1], run[m][1][i0 + 1], run[m][2][i0 + 1], run[m][3][i0 + 1]);
+                }
+            }
+            if (!DOT && p.partCol) {
+                csum = f4_add(csum, f4_shfl_xor(csum, 1));
+                csum = f4_add(csum, f4_shfl_xor(csum, 2));
+                if (t == 0) *reinterpret_cast<float4*>(p.partCol + (size_t)bid * p.d + 32 * bx + 4 * g) = csum;
+            }
+        }
+        if (DOT) {
+            float* s_dot = reinterpret_cast<float*>(smem + p.bar_off + 192);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+            if (lane == 0) s_dot[bx] = active ? dot : 0.f;
+            named_sync(2, kSWarps * 32);
+            if (bx == 0 && lane == 0 && p.partDot) {
+                float tsum = 0.f;
+                for (int w = 0; w < kSWarps; ++w) tsum += s_dot[w];
+                p.partDot[bid] = tsum;
+            }
+        }
+        if (bid == 0 && bx == 0 && lane == 0) p.header[p.slot] = (int)gridDim.x;
+    }
+}
+
+template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmH, const StreamParams& p, size_t smem,
+               int grid, const char* name, cudaStream_t st) {
+    auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD>;
+    GCA_TRY(set_smem(kern, smem));
+    const int threads = 32 * (1 + (PROJ ? kSWarps : 0) + (WGRAD ? kSWarps : 0));
+    {
+        ProfScope ps(name, st);
+        GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmH, p));
+    }
+    GCA_LAUNCH_OK();
+    return GCA_OK;
+}
+
+template <int R>
+int launch_dense_stream_t(const DenseStreamArgs& a, cudaStream_t st) {
+    if constexpr (R != 16 && R != 32) {
+        return GCA_ERR_UNSUPPORTED;
+    } else {
+        const bool proj = a.W != nullptr, wgrad = a.H != nullptr, dot = wgrad && a.B != nullptr;
+        if (!tc_enabled() || !stream_enabled() || (!proj && !wgrad)) return GCA_ERR_UNSUPPORTED;
+        // small inputs are launch-bound: the register-fed kernels (no tensor maps, 2 CTAs per SM) serve them
+        if (a.d % 32 != 0 || a.d > 32 * kSWarps || a.n < 64 * kSRows) return GCA_ERR_UNSUPPORTED;
+        if ((a.lda % 4) != 0 || (reinterpret_cast<uintptr_t>(a.A) % 16) != 0) return GCA_ERR_UNSUPPORTED;
+        if (dot && ((a.ldb % 4) != 0 || (reinterpret_cast<uintptr_t>(a.B) % 16) != 0)) return GCA_ERR_UNSUPPORTED;
+        if (wgrad && (reinterpret_cast<uintptr_t>(a.H) % 16) != 0) return GCA_ERR_UNSUPPORTED;
+        // r = 32: projection + weight gradient in one CTA would need more than the 120 registers 17 warps leave a
+        // thread; the caller issues the two halves as separate launches
+        if (R == 32 && proj && wgrad) return GCA_ERR_UNSUPPORTED;
+        constexpr int NT = R / 8;
+        StreamParams p{};
+        p.W = a.W; p.rowscale = a.rowscale; p.scalar = a.scalar; p.out = a.out;
+        p.partG = a.partG; p.partCol = a.partCol; p.partDot = a.partDot; p.header = a.header; p.slot = a.slot;
+        p.n = a.n; p.d = a.d; p.nb = a.d / 32;
+        const uint32_t a_bytes = (uint32_t)p.nb * kSBox;
+        const uint32_t h_bytes = wgrad ? (uint32_t)(kSRows * R * 4) : 0u;
+        p.b_off = dot ? a_bytes : 0u;
+        p.h_off = a_bytes * (dot ? 2u : 1u);
+        p.stage_bytes = (p.h_off + h_bytes + 1023u) & ~1023u;
+        p.tx_bytes = p.h_off + h_bytes;
+        const size_t red_bytes = proj ? (size_t)2 * kSWarps * (2 * NT * 32) * 16 : 0;
+        const size_t fixed = red_bytes + 256 + 1024;                 // partials + barriers / dot scratch + alignment slack
+        int stages = (int)((227 * 1024 - fixed) / p.stage_bytes);
+        if (stages > 8) stages = 8;
+        if (stages < 2) return GCA_ERR_UNSUPPORTED;
+        p.stages = stages;
+        p.red_off = (uint32_t)stages * p.stage_bytes;
+        p.bar_off = p.red_off + (uint32_t)red_bytes;
+        const size_t smem = (size_t)p.bar_off + 256 + 1024;
+        CUtensorMap tmA, tmB, tmH;
+        if (!get_box_map(&tmA, a.A, a.n, a.d, a.lda, 32, kSRows, true)) return GCA_ERR_UNSUPPORTED;
+        tmB = tmA; tmH = tmA;
+        if (dot && !get_box_map(&tmB, a.B, a.n, a.d, a.ldb, 32, kSRows, true)) return GCA_ERR_UNSUPPORTED;
+        if (wgrad && !get_box_map(&tmH, a.H, a.n, R, R, R, kSRows, R == 32)) return GCA_ERR_UNSUPPORTED;
+        const int ntiles = (a.n + kSRows - 1) / kSRows;
+        const int grid = ntiles < num_sms() ? ntiles : num_sms();
+        if (proj && wgrad) {
+            if (a.w_is_rd) return GCA_ERR_UNSUPPORTED;               // only the backward pairs the two (W = Wu [d, r])
+            if constexpr (R == 16) return launch_one<R, true, true, false, false>(tmA, tmB, tmH, p, smem, grid, a.prof_name, st);
+            return GCA_ERR_UNSUPPORTED;
+        }
+        if (proj)
+            return a.w_is_rd ? launch_one<R, true, false, false, true>(tmA, tmB, tmH, p, smem, grid, a.prof_name, st)
+                             : launch_one<R, true, false, false, false>(tmA, tmB, tmH, p, smem, grid, a.prof_name, st);
+        return dot ? launch_one<R, false, true, true, false>(tmA, tmB, tmH, p, smem, grid, a.prof_name, st)
+                   : launch_one<R, false, true, false, false>(tmA, tmB, tmH, p, smem, grid, a.prof_name, st);
+    }
+}
+
+}  // namespace
+
+int launch_dense_stream(int r, const DenseStreamArgs& a, cudaStream_t st) {
+    GCA_DISPATCH_R(r, (launch_dense_stream_t<R_>(a, st)));
+}
+
+}  // namespace gca

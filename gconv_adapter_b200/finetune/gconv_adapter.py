@@ -34,18 +34,14 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-_SIZE_CACHE: dict = {}
-
-
-def _sizes(lib, n: int, d: int, r: int):
-    """(forward workspace bytes, backward workspace bytes) - cached, the C calls are pure functions."""
-    key = (n, d, r)
-    hit = _SIZE_CACHE.get(key)
+def _sizes(lib, graph: GraphStructure, d: int, r: int):
+    """(forward workspace bytes, backward workspace bytes) of one call on this graph - cached on the graph object
+    (they depend on its row count and on whether it has hub rows; the C calls are pure functions)."""
+    cache = graph.__dict__.setdefault("_ws_sizes", {})
+    hit = cache.get((d, r))
     if hit is None:
-        hit = (lib.gca_forward_workspace_bytes(n, d, r), lib.gca_backward_workspace_bytes(n, d, r))
-        if len(_SIZE_CACHE) > 256:
-            _SIZE_CACHE.clear()
-        _SIZE_CACHE[key] = hit
+        hit = (lib.gca_forward_workspace_bytes(graph.handle, d, r), lib.gca_backward_workspace_bytes(graph.handle, d, r))
+        cache[(d, r)] = hit
     return hit
 
 
@@ -75,9 +71,9 @@ class _GConvAdapterFunction(torch.autograd.Function):
         b_down, b_up = b_down.contiguous(), b_up.contiguous()
         silu = act == _cabi.ACT["silu"]
         y = torch.empty((n, d), dtype=torch.float32, device=dev)
-        # one allocation: [Z' | H2 | (H1) | projection scratch]
+        # one allocation: [Z' | H2 | (H1) | per-call workspace (projection scratch, hub partial sums)]
         rw = _align(4 * max(n, 1) * r)
-        ws_bytes = _sizes(lib, n, d, r)[0]
+        ws_bytes = _sizes(lib, graph, d, r)[0]
         buf = torch.empty((3 if silu else 2) * rw + ws_bytes, dtype=torch.uint8, device=dev)
         base = buf.data_ptr()
         zp_ptr, h2_ptr = base, base + rw
@@ -127,7 +123,7 @@ class _GConvAdapterFunction(torch.autograd.Function):
         g_bu = torch.empty((d,), dtype=torch.float32, device=dev)
         g_bd = torch.empty((r,), dtype=torch.float32, device=dev)
         g_s = torch.empty((1,), dtype=torch.float32, device=dev) if scalar is not None else None
-        ws = torch.empty(_sizes(lib, n, d, r)[1], dtype=torch.uint8, device=dev)
+        ws = torch.empty(_sizes(lib, ctx.graph, d, r)[1], dtype=torch.uint8, device=dev)
         _cabi.check(lib.gca_backward(ctx.graph.handle, g_y.data_ptr(), g_y.stride(0), x.data_ptr(), x.stride(0),
                                      zp_ptr, h1_ptr, h2_ptr, w_down.data_ptr(), w_up.data_ptr(),
                                      b_up.data_ptr(), _ptr(scalar), ctx.act, int(ctx.skip), ws.data_ptr(),

@@ -64,15 +64,20 @@ class CudaPhases:
         _cabi.check(self.lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out_local.data_ptr(),
                                              d, r, self._stream(x)), "gca_fwd_project")
 
-    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local):
-        _cabi.check(self.lib.gca_fwd_hop1(g.handle, p_full.data_ptr(), bd.data_ptr(), act, z_local.data_ptr(),
-                                          _ptr(h1_local), bd.shape[0], self._stream(p_full)), "gca_fwd_hop1")
+    def hub_scratch(self, g, device):
+        """Per-call scratch for the partial sums of hub rows (None when the graph has no row longer than 512)."""
+        nbytes = self.lib.gca_hub_scratch_bytes(g.handle)
+        return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes else None
 
-    def fwd_hop2_up(self, g, z_full, x, wu, bu, scalar, skip, h2_local, y):
+    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local, hub=None):
+        _cabi.check(self.lib.gca_fwd_hop1(g.handle, p_full.data_ptr(), bd.data_ptr(), act, z_local.data_ptr(),
+                                          _ptr(h1_local), _ptr(hub), bd.shape[0], self._stream(p_full)), "gca_fwd_hop1")
+
+    def fwd_hop2_up(self, g, z_full, x, wu, bu, scalar, skip, h2_local, y, hub=None):
         d, r = wu.shape
         _cabi.check(self.lib.gca_fwd_hop2_up(g.handle, z_full.data_ptr(), x.data_ptr(), x.stride(0), wu.data_ptr(),
                                              bu.data_ptr(), _ptr(scalar), int(skip), h2_local.data_ptr(), y.data_ptr(),
-                                             y.stride(0), d, r, self._stream(x)), "gca_fwd_hop2_up")
+                                             y.stride(0), _ptr(hub), d, r, self._stream(x)), "gca_fwd_hop2_up")
 
     def bwd_scratch(self, d, r, device):
         return torch.empty(self.lib.gca_bwd_scratch_bytes(d, r), dtype=torch.uint8, device=device)
@@ -93,18 +98,18 @@ class CudaPhases:
         _cabi.check(self.lib.gca_bwd_up_wgrad(g.handle, gy.data_ptr(), gy.stride(0), h2_local.data_ptr(),
                                               scratch.data_ptr(), d, r, self._stream(gy)), "gca_bwd_up_wgrad")
 
-    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch):
+    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch, hub=None):
         r = gh2_full.shape[1]
         _cabi.check(self.lib.gca_bwd_hop2(g.handle, gh2_full.data_ptr(), z_local.data_ptr(), _ptr(h1_local), act,
-                                          gh1_local.data_ptr(), scratch.data_ptr(), r, self._stream(gh2_full)),
+                                          gh1_local.data_ptr(), scratch.data_ptr(), _ptr(hub), r, self._stream(gh2_full)),
                     "gca_bwd_hop2")
 
-    def bwd_hop1_down(self, g, gh1_full, x, gy, wd, scalar, skip, gp_local, gx, scratch):
+    def bwd_hop1_down(self, g, gh1_full, x, gy, wd, scalar, skip, gp_local, gx, scratch, hub=None):
         r, d = wd.shape
         _cabi.check(self.lib.gca_bwd_hop1_down(g.handle, gh1_full.data_ptr(), x.data_ptr(), x.stride(0), gy.data_ptr(),
                                                gy.stride(0), wd.data_ptr(), _ptr(scalar), int(skip), gp_local.data_ptr(),
                                                _ptr(gx), gx.stride(0) if gx is not None else d, scratch.data_ptr(),
-                                               d, r, self._stream(x)), "gca_bwd_hop1_down")
+                                               _ptr(hub), d, r, self._stream(x)), "gca_bwd_hop1_down")
 
     def bwd_finalize(self, scratch, wu, bu, scalar, skip, g_wd, g_bd, g_wu, g_bu, g_s):
         d, r = wu.shape
@@ -137,14 +142,15 @@ class _PartitionedFunction(torch.autograd.Function):
         h2 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
         h1 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev) if act == _cabi.ACT["silu"] else None
         y = torch.empty((n, d), dtype=torch.float32, device=dev)
+        hub = backend.hub_scratch(graph, dev) if hasattr(backend, "hub_scratch") else None
         if n > 0:
             backend.fwd_project(graph, x, w_down, p_full[lo:lo + n])
         _all_gather_rows(p_full, lo, s, group)
         if n > 0:
-            backend.fwd_hop1(graph, p_full, b_down, act, z_full[lo:lo + n], h1)
+            backend.fwd_hop1(graph, p_full, b_down, act, z_full[lo:lo + n], h1, hub)
         _all_gather_rows(z_full, lo, s, group)
         if n > 0:
-            backend.fwd_hop2_up(graph, z_full, x, w_up, b_up, scalar, skip, h2, y)
+            backend.fwd_hop2_up(graph, z_full, x, w_up, b_up, scalar, skip, h2, y, hub)
         ctx.graph, ctx.act, ctx.skip, ctx.group, ctx.backend = graph, act, skip, group, backend
         ctx.meta = (world, s, lo, n, d, r)
         ctx.has_scalar, ctx.has_h1 = scalar is not None, h1 is not None
@@ -182,6 +188,7 @@ class _PartitionedFunction(torch.autograd.Function):
         # gH2' first, then its all-gather runs (on NCCL's stream) while the weight-gradient half of the same
         # phase - which does not need remote rows - keeps this GPU busy
         split = hasattr(backend, "bwd_up_project")
+        hub = backend.hub_scratch(graph, dev) if hasattr(backend, "hub_scratch") else None
         if n > 0:
             scratch = backend.bwd_scratch(d, r, dev)
             if split:
@@ -194,10 +201,10 @@ class _PartitionedFunction(torch.autograd.Function):
         if work is not None:
             work.wait()
         if n > 0:
-            backend.bwd_hop2(graph, gh2_full, z_full[lo:lo + n], h1, ctx.act, gh1_full[lo:lo + n], scratch)
+            backend.bwd_hop2(graph, gh2_full, z_full[lo:lo + n], h1, ctx.act, gh1_full[lo:lo + n], scratch, hub)
         _all_gather_rows(gh1_full, lo, s, group)
         if n > 0:
-            backend.bwd_hop1_down(graph, gh1_full, x, g_y, w_down, scalar, ctx.skip, gp, g_x, scratch)
+            backend.bwd_hop1_down(graph, gh1_full, x, g_y, w_down, scalar, ctx.skip, gp, g_x, scratch, hub)
             backend.bwd_finalize(scratch, w_up, b_up, scalar, ctx.skip, g_wd, g_bd, g_wu, g_bu,
                                  g_s if scalar is not None else None)
         if world > 1:

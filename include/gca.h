@@ -15,6 +15,9 @@
  *    is allocated by the library: the caller passes workspaces sized by the *_bytes calls.
  *  - return value: GCA_OK (0) or a negative gca_status; no exceptions cross the ABI.
  *  - fp32 row-major tensors; `ld*` is the row pitch in elements (>= d, multiple of 4).
+ *  - re-entrant per (graph handle, stream): a built handle is read-only; every byte a call scribbles on (projection
+ *    scratch, partial sums, the partial sums of hub rows) comes from the caller's per-call workspaces, so one handle
+ *    may serve several streams / threads / adapters at once (SURVEY.md section 8b "Threading").
  *  - node rows are partitioned: a graph handle covers rows [row_begin, row_end) of an
  *    N-node graph ("local rows", n = row_end - row_begin); neighbour ids stay global.
  *    A single-GPU run uses row_begin = 0, row_end = N.
@@ -38,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 1
+#define GCA_ABI_VERSION 2
 
 typedef void* gca_stream_t;               /* cudaStream_t */
 typedef struct gca_graph gca_graph;       /* opaque, host-side descriptor of device arrays */
@@ -96,6 +99,10 @@ int    gca_graph_get_view(const gca_graph* g, gca_graph_view* out /* host */);
 /* coef[e] = dis[row(e)] * dis[colidx[e]] for the forward CSR, in CSR order: the fp32
  * edge weights gcn_norm would produce.  Only valid for a full-graph handle (n == N). */
 int    gca_graph_edge_coef(const gca_graph* g, float* coef, gca_stream_t stream);
+/* Rows with more than 512 neighbours ("hubs") are pre-reduced per work item into per-CALL scratch of this many bytes
+ * (256 B aligned), passed as `hub_scratch` to every phase that walks the graph.  0 when the validated build
+ * (gca_graph_validate) found no hub row: hub_scratch may then be NULL. */
+size_t gca_hub_scratch_bytes(const gca_graph* g);
 
 /* -------- backbone propagation over the same handle --------
  * out[i, 0:D] = dis[i] * sum_{j in N(i)} dis[j] * X[j, 0:D]  for the handle's local rows; transpose = 1 uses the
@@ -117,18 +124,19 @@ int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, const float
 /* conv_down.propagate + bias + act_fn, result pre-scaled for the next hop.
  * H1_local may be NULL unless act == GCA_ACT_SILU (backward needs the pre-activation). */
 int gca_fwd_hop1(const gca_graph* g, const float* Pp_full /*[N,r]*/, const float* bd /*[r]*/, int act,
-                 float* Zp_local /*[n,r]*/, float* H1_local /*[n,r] or NULL*/, int32_t r,
+                 float* Zp_local /*[n,r]*/, float* H1_local /*[n,r] or NULL*/, void* hub_scratch, int32_t r,
                  gca_stream_t stream);
 /* conv_up (propagate at width r, then lin r -> d, + bias) + skip + scalar.
  * scalar may be NULL (= 1).  H2_local is saved for the backward. */
 int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full /*[N,r]*/, const float* X, int64_t ldx,
                     const float* Wu /*[d,r]*/, const float* bu /*[d]*/, const float* scalar /*[1] or NULL*/,
-                    int skip, float* H2_local /*[n,r]*/, float* Y, int64_t ldy,
+                    int skip, float* H2_local /*[n,r]*/, float* Y, int64_t ldy, void* hub_scratch,
                     int32_t d, int32_t r, gca_stream_t stream);
 
 /* -------- backward phases (autograd of the above) -------- */
 size_t gca_bwd_scratch_bytes(int32_t d, int32_t r);
-/* gH2'[i] = dis[i] * s * gY[i] Wu ; partial sums for gWu = s * gY^T H2 and gbu = s * sum_i gY[i] */
+/* gH2'[i] = dis[i] * s * gY[i] Wu ; partial sums for gWu = s * gY^T H2 and gbu = s * sum_i gY[i].
+ * One pass over gY serves both (gca_stream.cu) when d % 32 == 0, d <= 256, r = 16. */
 int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local,
                const float* Wu, const float* scalar, float* gH2p_local /*[n,r]*/,
                void* scratch, int32_t d, int32_t r, gca_stream_t stream);
@@ -142,13 +150,13 @@ int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg, const flo
 /* gH1'[j] = dis[j] * act'(.) * dis[j] * sum_{i in out(j)} gH2'[i] ; partial sums for gbd */
 int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full /*[N,r]*/, const float* Zp_local,
                  const float* H1_local /*NULL unless silu*/, int act, float* gH1p_local /*[n,r]*/,
-                 void* scratch, int32_t r, gca_stream_t stream);
+                 void* scratch, void* hub_scratch, int32_t r, gca_stream_t stream);
 /* gP[j] = dis[j] * sum_{i in out(j)} gH1'[i] ; gX = gP Wd [+ s * gY] ; partials for gWd = gP^T X
  * and for <gY, X> (needed by gscalar).  gX may be NULL (x does not require grad). */
 int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full /*[N,r]*/, const float* X, int64_t ldx,
                       const float* gY, int64_t ldg, const float* Wd, const float* scalar, int skip,
                       float* gP_local /*[n,r] workspace*/, float* gX, int64_t ldgx,
-                      void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+                      void* scratch, void* hub_scratch, int32_t d, int32_t r, gca_stream_t stream);
 /* Deterministic second-stage reduction of the partial sums into the parameter gradients.
  * Any output pointer may be NULL.  gscalar = <gY, X>(if skip) + <gY^T H2, Wu> + <sum gY, bu>. */
 int gca_bwd_finalize(const void* scratch, const float* Wu, const float* bu, const float* scalar, int skip,
@@ -156,13 +164,13 @@ int gca_bwd_finalize(const void* scratch, const float* Wu, const float* bu, cons
                      float* gscalar /*[1]*/, int32_t d, int32_t r, gca_stream_t stream);
 
 /* -------- single-GPU conveniences: the whole forward / backward on one stream -------- */
-size_t gca_forward_workspace_bytes(int32_t n, int32_t d, int32_t r);   /* P' scratch */
+size_t gca_forward_workspace_bytes(const gca_graph* g, int32_t d, int32_t r);   /* P' scratch + hub scratch */
 int gca_forward(const gca_graph* g, const float* X, int64_t ldx,
                 const float* Wd, const float* bd, const float* Wu, const float* bu, const float* scalar,
                 int act, int skip, void* workspace,
                 float* Zp_save, float* H1_save /*NULL unless silu*/, float* H2_save,
                 float* Y, int64_t ldy, int32_t d, int32_t r, gca_stream_t stream);
-size_t gca_backward_workspace_bytes(int32_t n, int32_t d, int32_t r);  /* gH2', gH1', gP + scratch */
+size_t gca_backward_workspace_bytes(const gca_graph* g, int32_t d, int32_t r);  /* gH2', gH1', gP + partial sums + hub scratch */
 int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, const float* X, int64_t ldx,
                  const float* Zp_save, const float* H1_save, const float* H2_save,
                  const float* Wd, const float* Wu, const float* bu, const float* scalar,

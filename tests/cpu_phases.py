@@ -36,13 +36,13 @@ class CpuPhases:
     def fwd_project(self, g, x, wd, out_local):
         out_local.copy_(g.dis[:, None] * (x @ wd.t()))
 
-    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local):
+    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local, hub=None):
         h = g.dis[:, None] * g.agg(p_full) + bd
         if h1_local is not None:
             h1_local[:h.shape[0]].copy_(h)
         z_local.copy_(g.dis[:, None] * _act(h, act))
 
-    def fwd_hop2_up(self, g, z_full, x, wu, bu, scalar, skip, h2_local, y):
+    def fwd_hop2_up(self, g, z_full, x, wu, bu, scalar, skip, h2_local, y, hub=None):
         h2 = g.dis[:, None] * g.agg(z_full)
         h2_local[:h2.shape[0]].copy_(h2)
         s = scalar if scalar is not None else torch.ones(1)
@@ -66,7 +66,7 @@ class CpuPhases:
         scratch["gu"] = gy.t() @ h2_local[:gy.shape[0]]
         scratch["col"] = gy.sum(0)
 
-    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch):
+    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch, hub=None):
         gz = g.dis[:, None] * g.agg(gh2_full, transpose=True)
         n = gz.shape[0]
         if act == 1:
@@ -78,7 +78,7 @@ class CpuPhases:
         scratch["bd"] = gz.sum(0)
         gh1_local.copy_(g.dis[:, None] * gz)
 
-    def bwd_hop1_down(self, g, gh1_full, x, gy, wd, scalar, skip, gp_local, gx, scratch):
+    def bwd_hop1_down(self, g, gh1_full, x, gy, wd, scalar, skip, gp_local, gx, scratch, hub=None):
         s = scalar if scalar is not None else torch.ones(1)
         gp = g.dis[:, None] * g.agg(gh1_full, transpose=True)
         if gx is not None:

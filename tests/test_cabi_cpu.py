@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_cabi.LIB_PATH)
     for name in _declared_symbols():
         assert hasattr(raw, name), name
-    assert lib.gca_abi_version() == 1
+    assert lib.gca_abi_version() == _cabi.ABI_VERSION == 2
     assert lib.gca_status_string(0) == b"ok"
     assert b"outside" in lib.gca_status_string(-4)
 
@@ -37,7 +37,8 @@ def test_size_queries_and_argument_validation():
     assert lib.gca_graph_workspace_bytes(10, 100, 50, 40) == 0          # row_end < row_begin
     assert lib.gca_graph_workspace_bytes(-1, 100, 0, 100) == 0
     assert lib.gca_bwd_scratch_bytes(256, 16) % 256 == 0
-    assert lib.gca_backward_workspace_bytes(1000, 256, 16) > lib.gca_bwd_scratch_bytes(256, 16)
+    assert lib.gca_backward_workspace_bytes(None, 256, 16) == 0 and lib.gca_forward_workspace_bytes(None, 256, 16) == 0
+    assert lib.gca_hub_scratch_bytes(None) == 0
     assert lib.gca_shape_is_fast(256, 16) == 1 and lib.gca_shape_is_fast(300, 16) == 1
     assert lib.gca_shape_is_fast(30, 16) == 0 and lib.gca_shape_is_fast(256, 5) == 0
     h = ctypes.c_void_p()
@@ -53,3 +54,10 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libgca.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _cabi.load()
+
+
+def test_library_name_carries_the_hash_of_its_sources():
+    """build() is content-addressed: the binary that is loaded was built from exactly the sources in the tree."""
+    from gconv_adapter_b200 import build
+    assert os.path.basename(_cabi.LIB_PATH) == f"libgca.{build.source_hash()}.so"
+    assert os.path.isfile(_cabi.LIB_PATH)

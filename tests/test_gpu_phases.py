@@ -39,3 +39,82 @@ def test_fwd_project_matches_fp64(n, d, r):
     out2 = torch.empty_like(out)
     _cabi.check(lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out2.data_ptr(), d, r, stream), "project")
     assert torch.equal(out, out2)
+
+
+def _alloc_u8(nbytes):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")
+
+
+@pytest.mark.parametrize("n,d,r", [(50001, 256, 16), (2049, 128, 16), (4100, 64, 16), (2048, 32, 16), (8195, 256, 32),
+                                   (169343, 256, 16), (1000, 256, 16), (3000, 300, 16), (2708, 64, 8)])
+@pytest.mark.parametrize("with_scalar", [True, False])
+def test_backward_dense_phases_match_fp64(n, d, r, with_scalar):
+    """gca_bwd_up (one pass over gY: gH2' = dis * s * gY Wu together with the gWu / gbu partials) and the
+    weight-gradient half of gca_bwd_hop1_down (gWd = gP^T X, <gY, X>), reduced by gca_bwd_finalize, against fp64.
+    Shapes with d % 32 == 0, d <= 256, r in {16, 32} and n >= 2048 run on the TMA-fed streaming family
+    (gca_stream.cu; r = 16 fuses projection and weight gradient in one launch); the others on the register-fed kernels."""
+    lib = _cabi.load()
+    g = _graph(n, seed=3)
+    arr = g.arrays()
+    dis = arr["dis"]
+    gen = torch.Generator(device="cuda").manual_seed(7 * n + d + r)
+    x = torch.randn(n, d, device="cuda", generator=gen)
+    gy = torch.randn(n, d, device="cuda", generator=gen)
+    h2 = torch.randn(n, r, device="cuda", generator=gen)
+    z = torch.randn(n, r, device="cuda", generator=gen).abs()          # relu mask all ones
+    wu = torch.randn(d, r, device="cuda", generator=gen) * 0.1
+    wd = torch.randn(r, d, device="cuda", generator=gen) * 0.1
+    bu = torch.randn(d, device="cuda", generator=gen) * 0.1
+    s = torch.tensor([1.3], device="cuda") if with_scalar else None
+    sp = s.data_ptr() if with_scalar else None
+    gh2 = torch.full((n, r), float("nan"), device="cuda")
+    gh1 = torch.empty(n, r, device="cuda")
+    gp = torch.empty(n, r, device="cuda")
+    gx = torch.empty(n, d, device="cuda")
+    scratch = _alloc_u8(lib.gca_bwd_scratch_bytes(d, r))
+    hub_bytes = lib.gca_hub_scratch_bytes(g.handle)
+    hub = _alloc_u8(hub_bytes) if hub_bytes else None
+    hp = hub.data_ptr() if hub is not None else None
+    st = torch.cuda.current_stream().cuda_stream
+    g_wd, g_wu = torch.empty(r, d, device="cuda"), torch.empty(d, r, device="cuda")
+    g_bd, g_bu = torch.empty(r, device="cuda"), torch.empty(d, device="cuda")
+    g_s = torch.empty(1, device="cuda") if with_scalar else None
+
+    def run():
+        _cabi.check(lib.gca_bwd_up(g.handle, gy.data_ptr(), gy.stride(0), h2.data_ptr(), wu.data_ptr(), sp, gh2.data_ptr(),
+                                   scratch.data_ptr(), d, r, st), "bwd_up")
+        _cabi.check(lib.gca_bwd_hop2(g.handle, gh2.data_ptr(), z.data_ptr(), None, 1, gh1.data_ptr(), scratch.data_ptr(), hp, r, st),
+                    "bwd_hop2")
+        _cabi.check(lib.gca_bwd_hop1_down(g.handle, gh1.data_ptr(), x.data_ptr(), x.stride(0), gy.data_ptr(), gy.stride(0),
+                                          wd.data_ptr(), sp, 1, gp.data_ptr(), gx.data_ptr(), gx.stride(0), scratch.data_ptr(), hp,
+                                          d, r, st), "bwd_hop1_down")
+        _cabi.check(lib.gca_bwd_finalize(scratch.data_ptr(), wu.data_ptr(), bu.data_ptr(), sp, 1, g_wd.data_ptr(), g_bd.data_ptr(),
+                                         g_wu.data_ptr(), g_bu.data_ptr(), g_s.data_ptr() if with_scalar else None, d, r, st),
+                    "bwd_finalize")
+        torch.cuda.synchronize()
+
+    run()
+    sv = 1.3 if with_scalar else 1.0
+    X, GY, H2, WU, BU = x.double(), gy.double(), h2.double(), wu.double(), bu.double()
+
+    def rel(a, b):
+        return ((a.double() - b).abs().max() / b.abs().max()).item()
+
+    errs = {
+        "gH2'": rel(gh2, dis.double()[:, None] * sv * (GY @ WU)),
+        "gWu": rel(g_wu, sv * (GY.t() @ H2)),
+        "gbu": rel(g_bu, sv * GY.sum(0)),
+        "gWd": rel(g_wd, gp.double().t() @ X),                           # gP as the kernels produced it
+        "gX": rel(gx, gp.double() @ wd.double() + sv * GY),
+    }
+    if with_scalar:
+        errs["gs"] = rel(g_s, ((GY * X).sum() + ((GY.t() @ H2) * WU).sum() + (GY.sum(0) * BU).sum()).reshape(1))
+    print(f"backward dense phases n={n} d={d} r={r}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    assert torch.isfinite(gh2).all()
+    for k, v in errs.items():
+        assert v < 2e-6, f"{k}: max err / max|ref| = {v:.3e}"
+    # bitwise reproducible (fixed reduction orders, no atomics)
+    keep = [t.clone() for t in (gh2, g_wd, g_wu, g_bu, gx)]
+    run()
+    for a, b in zip(keep, (gh2, g_wd, g_wu, g_bu, gx)):
+        assert torch.equal(a, b)
