@@ -13,8 +13,10 @@
 //   warp 0        producer: one thread issues the boxes of tile k + stages - 1 as soon as all consumers released the stage
 //   warps 1-8     projection (if PROJ): warp w owns the 32-column box w of every tile (W fragments for those 32 k's
 //                 live in registers, split into tf32 hi / lo once), multiplies both 16-row m-tiles of the tile and
-//                 leaves a [32, R] partial in shared memory; after a named barrier four of the eight warps
-//                 (alternating) add the eight partials in box order, scale and store the rows.
+//                 leaves a [32, R] partial in one of two shared-memory buffers (mbarrier red_full / red_free).
+//   warps 9-10    projection epilogue (if PROJ): add the eight partials of a tile in box order, scale by
+//                 rowscale * s (prefetched before the wait) and store the rows - the MMA warps never wait for it
+//                 unless they run two tiles ahead.
 //   next 8 warps  weight gradient (if WGRAD): warp w owns the same box w as the N dimension (32 columns = 4 n-tiles),
 //                 K = the 32 rows of the tile (4 k-steps), M = R.  The H tile [32, R] arrives through its own
 //                 tensor map in the same stage.  Accumulators stay in registers for the whole kernel (folded into a
@@ -40,6 +42,9 @@ constexpr int kSRows = 32;                 // rows per tile
 constexpr int kSBox = 32 * kSRows * 4;     // one 32-column box of a tile: 4 KB, SWIZZLE_128B
 constexpr int kSWarps = 8;                 // consumer warps per role = column boxes of a 256-wide tile
 constexpr int kSFold = 4;                  // tiles between two folds of the tensor-core accumulators
+constexpr int kSEpi = 2;                   // epilogue warps of the projection role
+
+constexpr int stream_threads(bool proj, bool wgrad) { return 32 * (1 + (proj ? kSWarps + kSEpi : 0) + (wgrad ? kSWarps : 0)); }
 
 struct StreamParams {
     const float* W; const float* rowscale; const float* scalar; float* out;
@@ -53,7 +58,7 @@ __device__ __forceinline__ uint32_t box_off(int row, int chunk) { return (uint32
 __device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 
 template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD>
-__global__ void __launch_bounds__(32 * (1 + (PROJ ? kSWarps : 0) + (WGRAD ? kSWarps : 0)), 1)
+__global__ void __launch_bounds__(stream_threads(PROJ, WGRAD), 1)
 k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const StreamParams p) {
     constexpr int NT = R / 8, MT = R / 16;
@@ -63,9 +68,12 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bar0 = smem_addr(smem + p.bar_off);
     auto full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto empty = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
+    auto red_full = [&](int b) { return bar0 + 8u * (uint32_t)(2 * p.stages + b); };        // 8 MMA warps -> epilogue
+    auto red_free = [&](int b) { return bar0 + 8u * (uint32_t)(2 * p.stages + 2 + b); };    // epilogue -> MMA warps
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), kConsumers); }
+        for (int b = 0; b < 2; ++b) { mbar_init(red_full(b), kSWarps); mbar_init(red_free(b), kSEpi); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -125,7 +133,6 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 split_tf32(w1, wf[ks][nt][1], wf[ks][nt][3]);
             }
         }
-        const float sc_s = p.scalar ? __ldg(p.scalar) : 1.f;
         const int pg = (g >> 1) + 4 * (g & 1);
         float4* red = reinterpret_cast<float4*>(smem + p.red_off);          // [2][kSWarps][2 NT][32]
         constexpr int kSlots = 2 * NT * 32;                                  // float4 per partial
@@ -173,7 +180,10 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty(s));                            // this warp is done with the stage
-            float4* mine = red + ((size_t)(k & 1) * kSWarps + bx) * kSlots;
+            // hand the [32, R] partial of this warp's 32 k's to the epilogue warps (two buffers)
+            const int rbuf = k & 1;
+            if (k >= 2) mbar_wait(red_free(rbuf), (uint32_t)(((k >> 1) - 1) & 1));
+            float4* mine = red + ((size_t)rbuf * kSWarps + bx) * kSlots;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -181,36 +191,76 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mine[(mt * NT + nt) * 32 + lane] =
                         make_float4(acc[0][mt][nt][0] + acc[1][mt][nt][0], acc[0][mt][nt][1] + acc[1][mt][nt][1],
                                     acc[0][mt][nt][2] + acc[1][mt][nt][2], acc[0][mt][nt][3] + acc[1][mt][nt][3]);
-            named_sync(1, kSWarps * 32);
-            // Two partial buffers: a warp may already be writing tile k+1 into the other one while the reducers of
-            // tile k read this one, and nobody reaches tile k+2 before every reducer of tile k passed barrier k+1.
-            if ((bx >> 2) == (k & 1)) {
-                const float4* rb = red + (size_t)(k & 1) * kSWarps * kSlots;
-                for (int idx = (bx & 3) * 32 + lane; idx < kSlots; idx += 128) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(red_full(rbuf));                      // release: the epilogue acquires through its wait
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        return;
+    }
+
+    if (PROJ && cw < kSWarps + kSEpi) {
+        // ===================== projection epilogue warps =====================
+        constexpr int kSlots = 2 * NT * 32;
+        constexpr int kPer = kSlots / (kSEpi * 32);                          // fragment slots per thread (2 at r = 16)
+        const float4* red = reinterpret_cast<const float4*>(smem + p.red_off);
+        const float sc_s = p.scalar ? __ldg(p.scalar) : 1.f;
+        const int th = (cw - kSWarps) * 32 + lane;
+        // row scales (dis: cold in HBM, a fresh line per tile) are fetched kAhead tiles ahead into a register ring, so
+        // the epilogue never serialises a DRAM round trip per tile
+        constexpr int kAhead = 3;
+        float ring_a[kAhead][kPer], ring_b[kAhead][kPer];
+        auto row_of = [&](int k, int u) {
+            const int idx = th + u * kSEpi * 32;
+            const int slot = idx >> 5, g2 = (idx & 31) >> 2;
+            return (t0 + k) * kSRows + 16 * (slot / NT) + (g2 >> 1) + 4 * (g2 & 1);
+        };
+        auto fetch = [&](int k, float (&fa)[kPer], float (&fb)[kPer]) {
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int ra = row_of(k, u);
+                fa[u] = (k < my_tiles && ra < p.n && p.rowscale) ? __ldg(p.rowscale + ra) : 1.f;
+                fb[u] = (k < my_tiles && ra + 8 < p.n && p.rowscale) ? __ldg(p.rowscale + ra + 8) : 1.f;
+            }
+        };
+#pragma unroll
+        for (int a_ = 0; a_ < kAhead; ++a_) fetch(a_, ring_a[a_], ring_b[a_]);
+        for (int k0 = 0; k0 < my_tiles; k0 += kAhead) {
+#pragma unroll
+            for (int a_ = 0; a_ < kAhead; ++a_) {
+                const int k = k0 + a_;
+                if (k >= my_tiles) break;
+                const int rbuf = k & 1;
+                int row_a[kPer];
+                float sca[kPer], scb[kPer];
+#pragma unroll
+                for (int u = 0; u < kPer; ++u) { row_a[u] = row_of(k, u); sca[u] = ring_a[a_][u]; scb[u] = ring_b[a_][u]; }
+                fetch(k + kAhead, ring_a[a_], ring_b[a_]);                   // refill the slot just read
+                mbar_wait(red_full(rbuf), (uint32_t)((k >> 1) & 1));
+                const float4* rb = red + (size_t)rbuf * kSWarps * kSlots;
+#pragma unroll
+                for (int u = 0; u < kPer; ++u) {
+                    const int idx = th + u * kSEpi * 32;
                     float4 v = rb[idx];
 #pragma unroll
                     for (int w = 1; w < kSWarps; ++w) v = f4_add(v, rb[w * kSlots + idx]);   // box order: fixed
-                    const int slot = idx >> 5, ln = idx & 31, g2 = ln >> 2, t2 = ln & 3;
-                    const int mt = slot / NT, nt = slot - mt * NT;
-                    const int row_a = (t0 + k) * kSRows + 16 * mt + (g2 >> 1) + 4 * (g2 & 1), row_b = row_a + 8;
-                    if (row_a < p.n) {
-                        const float sc = (p.rowscale ? __ldg(p.rowscale + row_a) : 1.f) * sc_s;
-                        *reinterpret_cast<float2*>(p.out + (size_t)row_a * R + nt * 8 + 2 * t2) = make_float2(v.x * sc, v.y * sc);
-                    }
-                    if (row_b < p.n) {
-                        const float sc = (p.rowscale ? __ldg(p.rowscale + row_b) : 1.f) * sc_s;
-                        *reinterpret_cast<float2*>(p.out + (size_t)row_b * R + nt * 8 + 2 * t2) = make_float2(v.z * sc, v.w * sc);
-                    }
+                    const int slot = idx >> 5, t2 = idx & 3;
+                    const int nt = slot % NT;
+                    const float sa = sca[u] * sc_s, sb = scb[u] * sc_s;
+                    if (row_a[u] < p.n)
+                        *reinterpret_cast<float2*>(p.out + (size_t)row_a[u] * R + nt * 8 + 2 * t2) = make_float2(v.x * sa, v.y * sa);
+                    if (row_a[u] + 8 < p.n)
+                        *reinterpret_cast<float2*>(p.out + (size_t)(row_a[u] + 8) * R + nt * 8 + 2 * t2) = make_float2(v.z * sb, v.w * sb);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_free(rbuf));
             }
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         return;
     }
 
     if (WGRAD) {
         // ===================== weight-gradient warps =====================
-        const int bx = PROJ ? cw - kSWarps : cw;
+        const int bx = PROJ ? cw - kSWarps - kSEpi : cw;
         const bool active = bx < p.nb;
         float acc[MT][4][4], run[MT][4][4];
 #pragma unroll
@@ -325,7 +375,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
                int grid, const char* name, cudaStream_t st) {
     auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD>;
     GCA_TRY(set_smem(kern, smem));
-    const int threads = 32 * (1 + (PROJ ? kSWarps : 0) + (WGRAD ? kSWarps : 0));
+    const int threads = stream_threads(PROJ, WGRAD);
     {
         ProfScope ps(name, st);
         GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmH, p));
