@@ -8,11 +8,11 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 // K6: second-stage reduction of the per-CTA partials, fixed order.  A job = one block of 32 consecutive
-// column quads of one partial array (512 contiguous bytes per partial row: coalesced).  The 8 warps of a CTA
-// split the partial rows (warp w sums rows w, w+8, ... with 8 loads in flight), their 8 sums are added in warp
+// column quads of one partial array (512 contiguous bytes per partial row: coalesced).  The 32 warps of a CTA
+// split the partial rows (warp w sums rows w, w+32, ... with 8 loads in flight), their sums are added in warp
 // order through shared memory, and warp 0 writes the result.  The last CTA to finish adds up the gscalar pieces.
 // ------------------------------------------------------------------------------------------
-constexpr int kFinWarps = 16;
+constexpr int kFinWarps = 32;   // <= 148 + 148 partial rows per array: every warp sums its rows in ONE batch of loads
 __device__ __forceinline__ float4 sum_rows_strided(const float* __restrict__ base, int np, size_t pitch, int first, int stride,
                                                    bool ok) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -14,9 +14,10 @@
 //   warps 1-8     projection (if PROJ): warp w owns the 32-column box w of every tile (W fragments for those 32 k's
 //                 live in registers, split into tf32 hi / lo once), multiplies both 16-row m-tiles of the tile and
 //                 leaves a [32, R] partial in one of two shared-memory buffers (mbarrier red_full / red_free).
-//   warps 9-10    projection epilogue (if PROJ): add the eight partials of a tile in box order, scale by
-//                 rowscale * s (prefetched before the wait) and store the rows - the MMA warps never wait for it
-//                 unless they run two tiles ahead.
+//                 The tile's 32 row scales arrive with the tile (1D bulk copy into the stage) and are applied here.
+//   warps 9-10    projection epilogue (if PROJ): add the eight partials of a tile in box order and store the rows -
+//                 the MMA warps never wait for it unless they run two tiles ahead.  (No global load anywhere in the
+//                 consumers: a cold rowscale LDG per tile paced the whole kernel at one DRAM latency per tile.)
 //   next 8 warps  weight gradient (if WGRAD): warp w owns the same box w as the N dimension (32 columns = 4 n-tiles),
 //                 K = the 32 rows of the tile (4 k-steps), M = R.  The H tile [32, R] arrives through its own
 //                 tensor map in the same stage.  Accumulators stay in registers for the whole kernel (folded into a
@@ -31,6 +32,10 @@
 // 3xTF32 as everywhere: x = hi + lo, A B ~= A_hi B_hi + A_lo B_hi + A_hi B_lo (error ~2^-21 per product).
 //
 // Reference semantics: the two Linear layers of /root/reference/src/finetune/gconv_adapter.py:92 and their autograd.
+#include <cstdlib>
+
+#include <cuda_fp16.h>
+
 #include "gca_common.cuh"
 #include "gca_device.cuh"
 #include "gca_host.cuh"
@@ -44,25 +49,71 @@ constexpr int kSWarps = 8;                 // consumer warps per role = column b
 constexpr int kSFold = 4;                  // tiles between two folds of the tensor-core accumulators
 constexpr int kSEpi = 2;                   // epilogue warps of the projection role
 
-constexpr int stream_threads(bool proj, bool wgrad) { return 32 * (1 + (proj ? kSWarps + kSEpi : 0) + (wgrad ? kSWarps : 0)); }
+// MMA warps per box of the projection role (two - one 16-row m-tile each - measured no faster than one: 43.7 vs 44.0 us)
+__host__ __device__ constexpr int proj_split(int r, bool proj, bool wgrad) { return (void)r, (void)proj, (void)wgrad, 1; }
+__host__ __device__ constexpr int stream_threads(int r, bool proj, bool wgrad) {
+    return 32 * (1 + (proj ? kSWarps * proj_split(r, proj, wgrad) + kSEpi : 0) + (wgrad ? kSWarps : 0));
+}
 
 struct StreamParams {
     const float* W; const float* rowscale; const float* scalar; float* out;
     float* partG; float* partCol; float* partDot; int* header; int slot;
     int n, d, nb, stages;
-    uint32_t stage_bytes, b_off, h_off, tx_bytes, red_off, bar_off;
+    uint32_t stage_bytes, b_off, h_off, sc_off, tx_bytes, red_off, bar_off;
 };
 
 // byte offset of the 16-byte chunk `chunk` of row `row` inside a box of 128-byte rows with the 128-byte swizzle
 __device__ __forceinline__ uint32_t box_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 __device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 
-template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD>
-__global__ void __launch_bounds__(stream_threads(PROJ, WGRAD), 1)
+// ---- scaled 2xFP16 split (F16 = true) ------------------------------------------------------------------------
+// The legacy tensor path issues an f16 m16n8k16 at the rate of a tf32 m16n8k8 (8.6 clk per sub-core, measured:
+// experiments/mma_rate.cu), i.e. twice the k's per instruction.  fp16 and tf32 carry the same 11 significant bits, so
+//     x * 2^e = h0 + h1,  h0 = fp16_rn(x * 2^e),  h1 = fp16_rn(x * 2^e - h0)         A B ~= A0 B0 + A1 B0 + A0 B1
+// has the accuracy of the 3xTF32 split (~2^-22 per product) at HALF the tensor-core instructions.  What fp16 lacks is
+// range, so every operand block is scaled by an exact power of two that puts its largest magnitude in [2^13, 2^14):
+// per 32 x 32 box of the streamed tile (one warp owns a box: a warp-shuffle max, no cross-warp traffic), per H tile, per
+// warp for its W fragments.  An element 2^-20 below its block maximum still keeps all 11 bits of h0; below that only
+// the absolute error 2^-25 * 2^-e of fp16 subnormals remains, i.e. < 2^-38 of the block maximum.  Accumulators hold
+// scaled values and are unscaled (two exact power-of-two multiplies) when they leave the tensor core: per tile.
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float warp_max(float m) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    return m;
+}
+__device__ __forceinline__ float absmax4(float m, const float4& v) {
+    return fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
+// scale = 2^(13 - e), inv = 2^(e - 13) for amax = m * 2^e, 1 <= m < 2 (blocks of zeros / denormals: the largest normal scale)
+__device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
+    int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+    e = e < 14 ? 14 : e;
+    scale = __uint_as_float((uint32_t)(267 - e) << 23);
+    inv = __uint_as_float((uint32_t)(e - 13) << 23);
+}
+// (x0, x1) * scale -> packed halves {low = element 0}: hi = rn(.), lo = rn(. - hi)
+__device__ __forceinline__ void split_h2(float x0, float x1, float scale, uint32_t& hi, uint32_t& lo) {
+    const float a0 = x0 * scale, a1 = x1 * scale;
+    const __half2 h = __floats2half2_rn(a0, a1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD, bool F16>
+__global__ void __launch_bounds__(stream_threads(R, PROJ, WGRAD), 1)
 k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const StreamParams p) {
     constexpr int NT = R / 8, MT = R / 16;
-    constexpr int kConsumers = (PROJ ? kSWarps : 0) + (WGRAD ? kSWarps : 0);
+    constexpr int PW = proj_split(R, PROJ, WGRAD);          // MMA warps per box of the projection role
+    constexpr int kProjWarps = kSWarps * PW;
+    constexpr int kConsumers = (PROJ ? kProjWarps : 0) + (WGRAD ? kSWarps : 0);
     extern __shared__ uint8_t smem_unaligned[];
     uint8_t* smem = smem_unaligned + ((1024u - (smem_addr(smem_unaligned) & 1023u)) & 1023u);
     const uint32_t bar0 = smem_addr(smem + p.bar_off);
@@ -73,7 +124,7 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), kConsumers); }
-        for (int b = 0; b < 2; ++b) { mbar_init(red_full(b), kSWarps); mbar_init(red_free(b), kSEpi); }
+        for (int b = 0; b < 2; ++b) { mbar_init(red_full(b), kProjWarps); mbar_init(red_free(b), kSEpi); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -103,6 +154,9 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (DOT)
                     for (int b = 0; b < p.nb; ++b) tma_load_box(dst + p.b_off + (uint32_t)(b * kSBox), &tmB, b * 32, row0, full(s), pol);
                 if (WGRAD) tma_load_box_nohint(dst + p.h_off, &tmH, 0, row0, full(s));
+                // the tile's 32 row scales travel with the tile (rows past n read padding of the same allocation and
+                // are never used): no consumer ever waits on a cold global load
+                if (PROJ && p.rowscale) bulk_load_1d(dst + p.sc_off, p.rowscale + row0, kSRows * 4, full(s));
                 if (++s == p.stages) { s = 0; ++use; }
             }
         }
@@ -111,29 +165,56 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cw = warp - 1;
     const int g = lane >> 2, t = lane & 3;
 
-    if (PROJ && cw < kSWarps) {
+    if (PROJ && cw < kProjWarps) {
         // ===================== projection warps =====================
-        const int bx = cw;
+        const int bx = cw % kSWarps;
+        const int mt_lo = PW == 2 ? cw / kSWarps : 0, mt_hi = PW == 2 ? mt_lo + 1 : 2;   // m-tiles of this warp
         const bool active = bx < p.nb;
-        // W fragments of this warp's 32 k's: wf[ks][nt] = {hi(k0,c), hi(k1,c), lo(k0,c), lo(k1,c)},
-        // k0 = 32 bx + 16 (ks >> 1) + 4 t + 2 (ks & 1), k1 = k0 + 1, c = 8 nt + g
-        uint32_t wf[4][NT][4];
+        // W fragments of this warp's 32 k's, in registers for the whole kernel.
+        //  tf32: wf[ks][nt] = {hi(k0,c), hi(k1,c), lo(k0,c), lo(k1,c)}, k0 = 32 bx + 16 (ks >> 1) + 4 t + 2 (ks & 1), k1 = k0 + 1
+        //  fp16: wf[kb2][nt] = {hi(c0,c0+1), hi(c0+2,c0+3), lo(c0,c0+1), lo(c0+2,c0+3)} (packed pairs), c0 = 32 bx + 16 kb2 + 4 t,
+        //        scaled by this warp's own power of two (inv_w undoes it); in both cases c = 8 nt + g
+        constexpr int KS = F16 ? 2 : 4;
+        uint32_t wf[KS][NT][4];
+        float inv_w = 1.f;
+        auto wload = [&](int k_, int c) -> float {
+            if (!active) return 0.f;
+            return W_IS_RD ? __ldg(p.W + (size_t)c * p.d + k_) : __ldg(p.W + (size_t)k_ * R + c);
+        };
+        if constexpr (F16) {
+            float wv[2][NT][4];
+            float m = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const int k0 = 32 * bx + 16 * (ks >> 1) + 4 * t + 2 * (ks & 1);
+            for (int kb2 = 0; kb2 < 2; ++kb2)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int c = nt * 8 + g;
-                float w0 = 0.f, w1 = 0.f;
-                if (active) {
-                    w0 = W_IS_RD ? __ldg(p.W + (size_t)c * p.d + k0) : __ldg(p.W + (size_t)k0 * R + c);
-                    w1 = W_IS_RD ? __ldg(p.W + (size_t)c * p.d + k0 + 1) : __ldg(p.W + (size_t)(k0 + 1) * R + c);
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        wv[kb2][nt][e] = wload(32 * bx + 16 * kb2 + 4 * t + e, nt * 8 + g);
+                        m = fmaxf(m, fabsf(wv[kb2][nt][e]));
+                    }
+            float sw;
+            pow2_scale(warp_max(m), sw, inv_w);
+#pragma unroll
+            for (int kb2 = 0; kb2 < 2; ++kb2)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    split_h2(wv[kb2][nt][0], wv[kb2][nt][1], sw, wf[kb2][nt][0], wf[kb2][nt][2]);
+                    split_h2(wv[kb2][nt][2], wv[kb2][nt][3], sw, wf[kb2][nt][1], wf[kb2][nt][3]);
                 }
-                split_tf32(w0, wf[ks][nt][0], wf[ks][nt][2]);
-                split_tf32(w1, wf[ks][nt][1], wf[ks][nt][3]);
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int k0 = 32 * bx + 16 * (ks >> 1) + 4 * t + 2 * (ks & 1);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    split_tf32(wload(k0, nt * 8 + g), wf[ks][nt][0], wf[ks][nt][2]);
+                    split_tf32(wload(k0 + 1, nt * 8 + g), wf[ks][nt][1], wf[ks][nt][3]);
+                }
             }
         }
         const int pg = (g >> 1) + 4 * (g & 1);
+        const float sc_s = p.scalar ? __ldg(p.scalar) : 1.f;
         float4* red = reinterpret_cast<float4*>(smem + p.red_off);          // [2][kSWarps][2 NT][32]
         constexpr int kSlots = 2 * NT * 32;                                  // float4 per partial
         int s = 0;
@@ -149,38 +230,83 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[a_][mt][nt][i] = 0.f;
             mbar_wait(full(s), ph);
+            float inv_x = 1.f;                                               // undoes the box scale of the fp16 path
             if (active) {
                 const uint8_t* box = smem + (size_t)s * p.stage_bytes + bx * kSBox;
+                if constexpr (F16) {
+                    // the whole (half) box first: its largest magnitude fixes the scale
+                    float4 x[2][2][2];                                       // [kb2][mt][row g / g + 8]
+                    float m = 0.f;
 #pragma unroll
-                for (int kb2 = 0; kb2 < 2; ++kb2) {
+                    for (int kb2 = 0; kb2 < 2; ++kb2)
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const int r_lo = 16 * mt + pg, r_hi = r_lo + 8;
-                        const float4 x0 = lds4(box + box_off(r_lo, 4 * kb2 + t));
-                        const float4 x1 = lds4(box + box_off(r_hi, 4 * kb2 + t));
-                        const float e0[4] = {x0.x, x0.y, x0.z, x0.w};
-                        const float e1[4] = {x1.x, x1.y, x1.z, x1.w};
+                        for (int mt = 0; mt < 2; ++mt) {
+                            if (mt < mt_lo || mt >= mt_hi) continue;
+                            x[kb2][mt][0] = lds4(box + box_off(16 * mt + pg, 4 * kb2 + t));
+                            x[kb2][mt][1] = lds4(box + box_off(16 * mt + pg + 8, 4 * kb2 + t));
+                            m = absmax4(absmax4(m, x[kb2][mt][0]), x[kb2][mt][1]);
+                        }
+                    float sx;
+                    pow2_scale(warp_max(m), sx, inv_x);
 #pragma unroll
-                        for (int s2 = 0; s2 < 2; ++s2) {
+                    for (int kb2 = 0; kb2 < 2; ++kb2)
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            if (mt < mt_lo || mt >= mt_hi) continue;
+                            // one float4 per row = one k16 step: k = 2t, 2t+1 -> columns 4t, 4t+1 ; k = 2t+8, 2t+9 -> 4t+2, 4t+3
                             uint32_t ah[4], al[4];
-                            split_tf32(e0[2 * s2], ah[0], al[0]);        // (row g,   k = t)
-                            split_tf32(e1[2 * s2], ah[1], al[1]);        // (row g+8, k = t)
-                            split_tf32(e0[2 * s2 + 1], ah[2], al[2]);    // (row g,   k = t+4)
-                            split_tf32(e1[2 * s2 + 1], ah[3], al[3]);    // (row g+8, k = t+4)
-                            const int ks = kb2 * 2 + s2;
+                            split_h2(x[kb2][mt][0].x, x[kb2][mt][0].y, sx, ah[0], al[0]);
+                            split_h2(x[kb2][mt][1].x, x[kb2][mt][1].y, sx, ah[1], al[1]);
+                            split_h2(x[kb2][mt][0].z, x[kb2][mt][0].w, sx, ah[2], al[2]);
+                            split_h2(x[kb2][mt][1].z, x[kb2][mt][1].w, sx, ah[3], al[3]);
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt) {
-                                mma_tf32(acc[0][mt][nt], ah, wf[ks][nt][0], wf[ks][nt][1]);
-                                mma_tf32(acc[1][mt][nt], al, wf[ks][nt][0], wf[ks][nt][1]);
-                                mma_tf32(acc[1][mt][nt], ah, wf[ks][nt][2], wf[ks][nt][3]);
+                                mma_f16(acc[0][mt][nt], ah, wf[kb2][nt][0], wf[kb2][nt][1]);
+                                mma_f16(acc[1][mt][nt], al, wf[kb2][nt][0], wf[kb2][nt][1]);
+                                mma_f16(acc[1][mt][nt], ah, wf[kb2][nt][2], wf[kb2][nt][3]);
+                            }
+                        }
+                } else {
+#pragma unroll
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            if (mt < mt_lo || mt >= mt_hi) continue;
+                            const int r_lo = 16 * mt + pg, r_hi = r_lo + 8;
+                            const float4 x0 = lds4(box + box_off(r_lo, 4 * kb2 + t));
+                            const float4 x1 = lds4(box + box_off(r_hi, 4 * kb2 + t));
+                            const float e0[4] = {x0.x, x0.y, x0.z, x0.w};
+                            const float e1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                            for (int s2 = 0; s2 < 2; ++s2) {
+                                uint32_t ah[4], al[4];
+                                split_tf32(e0[2 * s2], ah[0], al[0]);        // (row g,   k = t)
+                                split_tf32(e1[2 * s2], ah[1], al[1]);        // (row g+8, k = t)
+                                split_tf32(e0[2 * s2 + 1], ah[2], al[2]);    // (row g,   k = t+4)
+                                split_tf32(e1[2 * s2 + 1], ah[3], al[3]);    // (row g+8, k = t+4)
+                                const int ks = kb2 * 2 + s2;
+#pragma unroll
+                                for (int nt = 0; nt < NT; ++nt) {
+                                    mma_tf32(acc[0][mt][nt], ah, wf[ks][nt][0], wf[ks][nt][1]);
+                                    mma_tf32(acc[1][mt][nt], al, wf[ks][nt][0], wf[ks][nt][1]);
+                                    mma_tf32(acc[1][mt][nt], ah, wf[ks][nt][2], wf[ks][nt][3]);
+                                }
                             }
                         }
                     }
                 }
             }
+            // row scales of this lane's rows (16 mt + pg, + 8), read before the stage is released
+            float sc[2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float* scs = reinterpret_cast<const float*>(smem + (size_t)s * p.stage_bytes + p.sc_off);
+                sc[mt][0] = (p.rowscale ? scs[16 * mt + pg] : 1.f) * sc_s * inv_w;
+                sc[mt][1] = (p.rowscale ? scs[16 * mt + pg + 8] : 1.f) * sc_s * inv_w;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty(s));                            // this warp is done with the stage
-            // hand the [32, R] partial of this warp's 32 k's to the epilogue warps (two buffers)
+            // hand the scaled [32, R] partial of this warp's 32 k's to the epilogue warps (two buffers)
             const int rbuf = k & 1;
             if (k >= 2) mbar_wait(red_free(rbuf), (uint32_t)(((k >> 1) - 1) & 1));
             float4* mine = red + ((size_t)rbuf * kSWarps + bx) * kSlots;
@@ -188,9 +314,9 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
-                    mine[(mt * NT + nt) * 32 + lane] =
-                        make_float4(acc[0][mt][nt][0] + acc[1][mt][nt][0], acc[0][mt][nt][1] + acc[1][mt][nt][1],
-                                    acc[0][mt][nt][2] + acc[1][mt][nt][2], acc[0][mt][nt][3] + acc[1][mt][nt][3]);
+                    if (mt >= mt_lo && mt < mt_hi) mine[(mt * NT + nt) * 32 + lane] =
+                        make_float4((acc[0][mt][nt][0] + acc[1][mt][nt][0]) * inv_x * sc[mt][0], (acc[0][mt][nt][1] + acc[1][mt][nt][1]) * inv_x * sc[mt][0],
+                                    (acc[0][mt][nt][2] + acc[1][mt][nt][2]) * inv_x * sc[mt][1], (acc[0][mt][nt][3] + acc[1][mt][nt][3]) * inv_x * sc[mt][1]);
             __syncwarp();
             if (lane == 0) mbar_arrive(red_full(rbuf));                      // release: the epilogue acquires through its wait
             if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -198,69 +324,37 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return;
     }
 
-    if (PROJ && cw < kSWarps + kSEpi) {
+    if (PROJ && cw < kProjWarps + kSEpi) {
         // ===================== projection epilogue warps =====================
         constexpr int kSlots = 2 * NT * 32;
         constexpr int kPer = kSlots / (kSEpi * 32);                          // fragment slots per thread (2 at r = 16)
         const float4* red = reinterpret_cast<const float4*>(smem + p.red_off);
-        const float sc_s = p.scalar ? __ldg(p.scalar) : 1.f;
-        const int th = (cw - kSWarps) * 32 + lane;
-        // row scales (dis: cold in HBM, a fresh line per tile) are fetched kAhead tiles ahead into a register ring, so
-        // the epilogue never serialises a DRAM round trip per tile
-        constexpr int kAhead = 3;
-        float ring_a[kAhead][kPer], ring_b[kAhead][kPer];
-        auto row_of = [&](int k, int u) {
-            const int idx = th + u * kSEpi * 32;
-            const int slot = idx >> 5, g2 = (idx & 31) >> 2;
-            return (t0 + k) * kSRows + 16 * (slot / NT) + (g2 >> 1) + 4 * (g2 & 1);
-        };
-        auto fetch = [&](int k, float (&fa)[kPer], float (&fb)[kPer]) {
+        const int th = (cw - kProjWarps) * 32 + lane;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int rbuf = k & 1;
+            mbar_wait(red_full(rbuf), (uint32_t)((k >> 1) & 1));
+            const float4* rb = red + (size_t)rbuf * kSWarps * kSlots;
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
-                const int ra = row_of(k, u);
-                fa[u] = (k < my_tiles && ra < p.n && p.rowscale) ? __ldg(p.rowscale + ra) : 1.f;
-                fb[u] = (k < my_tiles && ra + 8 < p.n && p.rowscale) ? __ldg(p.rowscale + ra + 8) : 1.f;
+                const int idx = th + u * kSEpi * 32;
+                float4 v = rb[idx];
+#pragma unroll
+                for (int w = 1; w < kSWarps; ++w) v = f4_add(v, rb[w * kSlots + idx]);   // box order: fixed
+                const int slot = idx >> 5, g2 = (idx & 31) >> 2, t2 = idx & 3;
+                const int mt = slot / NT, nt = slot - mt * NT;
+                const int row_a = (t0 + k) * kSRows + 16 * mt + (g2 >> 1) + 4 * (g2 & 1);
+                if (row_a < p.n) *reinterpret_cast<float2*>(p.out + (size_t)row_a * R + nt * 8 + 2 * t2) = make_float2(v.x, v.y);
+                if (row_a + 8 < p.n) *reinterpret_cast<float2*>(p.out + (size_t)(row_a + 8) * R + nt * 8 + 2 * t2) = make_float2(v.z, v.w);
             }
-        };
-#pragma unroll
-        for (int a_ = 0; a_ < kAhead; ++a_) fetch(a_, ring_a[a_], ring_b[a_]);
-        for (int k0 = 0; k0 < my_tiles; k0 += kAhead) {
-#pragma unroll
-            for (int a_ = 0; a_ < kAhead; ++a_) {
-                const int k = k0 + a_;
-                if (k >= my_tiles) break;
-                const int rbuf = k & 1;
-                int row_a[kPer];
-                float sca[kPer], scb[kPer];
-#pragma unroll
-                for (int u = 0; u < kPer; ++u) { row_a[u] = row_of(k, u); sca[u] = ring_a[a_][u]; scb[u] = ring_b[a_][u]; }
-                fetch(k + kAhead, ring_a[a_], ring_b[a_]);                   // refill the slot just read
-                mbar_wait(red_full(rbuf), (uint32_t)((k >> 1) & 1));
-                const float4* rb = red + (size_t)rbuf * kSWarps * kSlots;
-#pragma unroll
-                for (int u = 0; u < kPer; ++u) {
-                    const int idx = th + u * kSEpi * 32;
-                    float4 v = rb[idx];
-#pragma unroll
-                    for (int w = 1; w < kSWarps; ++w) v = f4_add(v, rb[w * kSlots + idx]);   // box order: fixed
-                    const int slot = idx >> 5, t2 = idx & 3;
-                    const int nt = slot % NT;
-                    const float sa = sca[u] * sc_s, sb = scb[u] * sc_s;
-                    if (row_a[u] < p.n)
-                        *reinterpret_cast<float2*>(p.out + (size_t)row_a[u] * R + nt * 8 + 2 * t2) = make_float2(v.x * sa, v.y * sa);
-                    if (row_a[u] + 8 < p.n)
-                        *reinterpret_cast<float2*>(p.out + (size_t)(row_a[u] + 8) * R + nt * 8 + 2 * t2) = make_float2(v.z * sb, v.w * sb);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(red_free(rbuf));
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(red_free(rbuf));
         }
         return;
     }
 
     if (WGRAD) {
         // ===================== weight-gradient warps =====================
-        const int bx = PROJ ? cw - kSWarps - kSEpi : cw;
+        const int bx = PROJ ? cw - kProjWarps - kSEpi : cw;
         const bool active = bx < p.nb;
         float acc[MT][4][4], run[MT][4][4];
 #pragma unroll
@@ -294,6 +388,76 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint8_t* boxA = stg + bx * kSBox;
                 const uint8_t* boxB = stg + p.b_off + bx * kSBox;
                 const uint8_t* ht = stg + p.h_off;
+                if constexpr (F16) {
+                    // the whole box first (its largest magnitude fixes the scale): k16 step ks2 covers rows 16 ks2 .. + 15,
+                    // k = 2t, 2t+1, 2t+8, 2t+9 -> rows rA, rB, 8 + rA, 8 + rB (the same conflict-free row sets as the tf32 path)
+                    float4 v[2][4];
+                    float mb = 0.f;
+#pragma unroll
+                    for (int ks2 = 0; ks2 < 2; ++ks2)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = 16 * ks2 + 8 * (q >> 1) + ((q & 1) ? rB : rA);
+                            v[ks2][q] = lds4(boxA + box_off(row, g));
+                            mb = absmax4(mb, v[ks2][q]);
+                            if (DOT) {
+                                const float4 w = lds4(boxB + box_off(row, g));
+                                dot = fmaf(v[ks2][q].x, w.x, fmaf(v[ks2][q].y, w.y, fmaf(v[ks2][q].z, w.z, fmaf(v[ks2][q].w, w.w, dot))));
+                            } else {
+                                csum = f4_add(csum, v[ks2][q]);
+                            }
+                        }
+                    float hv[2][MT][8];
+                    float mh = 0.f;
+#pragma unroll
+                    for (int ks2 = 0; ks2 < 2; ++ks2)
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int row = 16 * ks2 + 8 * (q >> 2) + ((q & 1) ? rB : rA);
+                                hv[ks2][m][q] = hload(ht, row, 16 * m + g + 8 * ((q >> 1) & 1));
+                                mh = fmaxf(mh, fabsf(hv[ks2][m][q]));
+                            }
+                    float sb, inv_b, sh, inv_h;
+                    pow2_scale(warp_max(mb), sb, inv_b);
+                    pow2_scale(warp_max(mh), sh, inv_h);
+#pragma unroll
+                    for (int ks2 = 0; ks2 < 2; ++ks2) {
+                        uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+                        const float e0[4] = {v[ks2][0].x, v[ks2][0].y, v[ks2][0].z, v[ks2][0].w};
+                        const float e1[4] = {v[ks2][1].x, v[ks2][1].y, v[ks2][1].z, v[ks2][1].w};
+                        const float e2[4] = {v[ks2][2].x, v[ks2][2].y, v[ks2][2].z, v[ks2][2].w};
+                        const float e3[4] = {v[ks2][3].x, v[ks2][3].y, v[ks2][3].z, v[ks2][3].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            split_h2(e0[j], e1[j], sb, bh0[j], bl0[j]);          // k = 2t, 2t+1   (n-tile j)
+                            split_h2(e2[j], e3[j], sb, bh1[j], bl1[j]);          // k = 2t+8, 2t+9
+                        }
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            uint32_t ah[4], al[4];
+                            split_h2(hv[ks2][m][0], hv[ks2][m][1], sh, ah[0], al[0]);   // c = g,   k = 2t, 2t+1
+                            split_h2(hv[ks2][m][2], hv[ks2][m][3], sh, ah[1], al[1]);   // c = g+8
+                            split_h2(hv[ks2][m][4], hv[ks2][m][5], sh, ah[2], al[2]);   // c = g,   k = 2t+8, 2t+9
+                            split_h2(hv[ks2][m][6], hv[ks2][m][7], sh, ah[3], al[3]);   // c = g+8
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mma_f16(acc[m][j], ah, bh0[j], bh1[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mma_f16(acc[m][j], al, bh0[j], bh1[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mma_f16(acc[m][j], ah, bl0[j], bl1[j]);
+                        }
+                    }
+                    // the accumulators hold box-scaled x tile-scaled values: unscale and fold every tile
+                    const float f = inv_b * inv_h;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { run[m][j][i] = fmaf(acc[m][j][i], f, run[m][j][i]); acc[m][j][i] = 0.f; }
+                } else {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const int ra = 8 * ks + rA, rb = 8 * ks + rB;
@@ -326,12 +490,13 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+                }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty(s));
-            if ((k % kSFold) == kSFold - 1) fold();
+            if (!F16 && (k % kSFold) == kSFold - 1) fold();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        fold();
+        if (!F16) fold();
         // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns 32 bx + 8t .. + 7 ----
         if (active) {
             float* pgp = p.partG + (size_t)bid * R * p.d;
@@ -373,11 +538,17 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmH, const StreamParams& p, size_t smem,
                int grid, const char* name, cudaStream_t st) {
-    auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD>;
-    GCA_TRY(set_smem(kern, smem));
-    const int threads = stream_threads(PROJ, WGRAD);
-    {
-        ProfScope ps(name, st);
+    // GCA_STREAM_TF32=1 selects the 3xTF32 products instead of the scaled 2xFP16 split (A/B runs, tests)
+    static const bool tf32 = [] { const char* e = getenv("GCA_STREAM_TF32"); return e && e[0] == '1'; }();
+    const int threads = stream_threads(R, PROJ, WGRAD);
+    ProfScope ps(name, st);
+    if (tf32) {
+        auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD, false>;
+        GCA_TRY(set_smem(kern, smem));
+        GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmH, p));
+    } else {
+        auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD, true>;
+        GCA_TRY(set_smem(kern, smem));
         GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmH, p));
     }
     GCA_LAUNCH_OK();
@@ -408,8 +579,10 @@ int launch_dense_stream_t(const DenseStreamArgs& a, cudaStream_t st) {
         const uint32_t h_bytes = wgrad ? (uint32_t)(kSRows * R * 4) : 0u;
         p.b_off = dot ? a_bytes : 0u;
         p.h_off = a_bytes * (dot ? 2u : 1u);
-        p.stage_bytes = (p.h_off + h_bytes + 1023u) & ~1023u;
-        p.tx_bytes = p.h_off + h_bytes;
+        p.sc_off = p.h_off + h_bytes;
+        const uint32_t sc_bytes = proj && a.rowscale ? (uint32_t)(kSRows * 4) : 0u;
+        p.stage_bytes = (p.sc_off + sc_bytes + 1023u) & ~1023u;
+        p.tx_bytes = p.sc_off + sc_bytes;
         const size_t red_bytes = proj ? (size_t)2 * kSWarps * (2 * NT * 32) * 16 : 0;
         const size_t fixed = red_bytes + 256 + 1024;                 // partials + barriers / dot scratch + alignment slack
         int stages = (int)((227 * 1024 - fixed) / p.stage_bytes);
