@@ -45,12 +45,14 @@ int num_sms();
 // Optional per-kernel timing with CUDA events recorded on the launching stream
 // (gca_profile_enable / gca_profile_report); off by default and free when off.
 bool prof_enabled();
-void prof_begin(const char* name, cudaStream_t st);
+void prof_begin(const char* name, const char* variant, cudaStream_t st);
 void prof_end(cudaStream_t st);
+// `variant` names the kernel implementation that was picked (reported by gca_profile_report, so that the tests can
+// assert which code path a run-time switch really selected).
 struct ProfScope {
     cudaStream_t st;
     bool on;
-    ProfScope(const char* name, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_begin(name, s); }
+    ProfScope(const char* name, cudaStream_t s, const char* variant = "") : st(s), on(prof_enabled()) { if (on) prof_begin(name, variant, s); }
     ~ProfScope() { if (on) prof_end(st); }
 };
 

@@ -629,7 +629,7 @@ int launch_hop_expand_t(const Csr& c, const float* F, const float* W,
                 const int ntiles_t = (n + kTcRows - 1) / kTcRows;
                 const int grid_t = ntiles_t < num_sms() ? ntiles_t : num_sms();
                 {
-                    ProfScope ps(prof_k3, st);
+                    ProfScope ps(prof_k3, st, "tcgen05");
                     GCA_CUDA(launch_pdl(k_hop_expand_tc<R, W_IS_DR>, dim3(grid_t), dim3(512), smem_tc, st, rowptr, colidx, dis, F, W, bias,
                                         resid, ldr, scalar, alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part, tm_x, tm_y,
                                         pregathered));
@@ -644,7 +644,7 @@ int launch_hop_expand_t(const Csr& c, const float* F, const float* W,
                 const int per_sm = smem_m <= 100 * 1024 ? 2 : 1;
                 const int grid_m = ntiles_m < per_sm * num_sms() ? ntiles_m : per_sm * num_sms();
                 {
-                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+                    ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st, "mma");
                     k_hop_expand_mma<R, W_IS_DR><<<grid_m, 256, smem_m, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
                                                                               alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part);
                 }
@@ -659,7 +659,7 @@ int launch_hop_expand_t(const Csr& c, const float* F, const float* W,
     const int ntiles = (n + kTileRows - 1) / kTileRows;
     const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
     {
-        ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st);
+        ProfScope ps(W_IS_DR ? "hop_expand_fwd" : "hop_expand_bwd", st, "ffma");
         k_hop_expand<R, W_IS_DR><<<grid, 256, smem, st>>>(rowptr, colidx, dis, F, W, bias, resid, ldr, scalar,
                                                            alpha_is_scalar, use_resid, Hout, Out, ldo, n, d, c.hubitem, c.hub_part);
     }

@@ -113,14 +113,14 @@ bool get_box_map(CUtensorMap* tm, const float* base, int rows, int cols, int64_t
     return true;
 }
 
-struct ProfEntry { const char* name; cudaEvent_t a, b; };
+struct ProfEntry { const char* name; const char* variant; cudaEvent_t a, b; };
 static std::atomic<bool> g_prof_on{false};
 static std::mutex g_prof_mu;
 static std::vector<ProfEntry> g_prof;
 
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
-void prof_begin(const char* name, cudaStream_t st) {
-    ProfEntry e{name, nullptr, nullptr};
+void prof_begin(const char* name, const char* variant, cudaStream_t st) {
+    ProfEntry e{name, variant ? variant : "", nullptr, nullptr};
     if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
     cudaEventRecord(e.a, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -141,25 +141,26 @@ extern "C" int gca_profile_enable(int on) {
     return GCA_OK;
 }
 
-// Synchronises the recorded events and writes {"name": {"launches": n, "ms": total}, ...} (JSON).
+// Synchronises the recorded events and writes {"name": {"launches": n, "ms": total, "variant": "..."}, ...} (JSON).
 extern "C" int gca_profile_report(char* buf, size_t n) {
     if (!buf || n == 0) return GCA_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(gca::g_prof_mu);
     std::map<std::string, std::pair<long, double>> acc;
+    std::map<std::string, std::string> variant;
     std::vector<std::string> order;
     for (auto& e : gca::g_prof) {
         if (cudaEventSynchronize(e.b) != cudaSuccess) continue;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) continue;
         auto it = acc.find(e.name);
-        if (it == acc.end()) { order.push_back(e.name); acc[e.name] = {1, ms}; }
+        if (it == acc.end()) { order.push_back(e.name); acc[e.name] = {1, ms}; variant[e.name] = e.variant; }
         else { it->second.first++; it->second.second += ms; }
     }
     std::string out = "{";
     for (size_t i = 0; i < order.size(); ++i) {
         char tmp[256];
-        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", i ? ", " : "", order[i].c_str(),
-                 acc[order[i]].first, acc[order[i]].second);
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"variant\": \"%s\"}", i ? ", " : "", order[i].c_str(),
+                 acc[order[i]].first, acc[order[i]].second, variant[order[i]].c_str());
         out += tmp;
     }
     out += "}";

@@ -242,7 +242,7 @@ int launch_project_t(const float* A, int64_t lda, const float* W, const float* r
                     int grid_m = (nmt + 7) / 8;
                     if (grid_m > 2 * num_sms()) grid_m = 2 * num_sms();
                     {
-                        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
+                        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st, "mma");
                         GCA_CUDA(launch_pdl(k_project_mma<R, W_IS_RD>, dim3(grid_m), dim3(256), smem_m, st, A, lda, W, rowscale, scalar, out, n, d));
                     }
                     GCA_LAUNCH_OK();
@@ -258,7 +258,7 @@ int launch_project_t(const float* A, int64_t lda, const float* W, const float* r
     const int ntiles = (n + TILE - 1) / TILE;
     const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
     {
-        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
+        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st, "ffma");
         k_project<R, W_IS_RD><<<grid, 256, smem, st>>>(A, lda, W, rowscale, scalar, out, n, d);
     }
     GCA_LAUNCH_OK();

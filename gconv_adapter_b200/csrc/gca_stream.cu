@@ -541,7 +541,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     // GCA_STREAM_TF32=1 selects the 3xTF32 products instead of the scaled 2xFP16 split (A/B runs, tests)
     static const bool tf32 = [] { const char* e = getenv("GCA_STREAM_TF32"); return e && e[0] == '1'; }();
     const int threads = stream_threads(R, PROJ, WGRAD);
-    ProfScope ps(name, st);
+    ProfScope ps(name, st, tf32 ? "stream_tf32" : "stream_f16");
     if (tf32) {
         auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD, false>;
         GCA_TRY(set_smem(kern, smem));

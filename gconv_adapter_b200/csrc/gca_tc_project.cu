@@ -280,7 +280,7 @@ int launch_project_tc_impl(const float* A, int64_t lda, const float* W, const fl
     const int ntiles = (n + kRows - 1) / kRows;
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
     {
-        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st);
+        ProfScope ps(W_IS_RD ? "project_fwd" : "project_bwd", st, "tcgen05");
         k_project_tc<R, W_IS_RD><<<grid, kThreads, smem, st>>>(A, lda, W, rowscale, scalar, out, n, d, nstage);
     }
     GCA_LAUNCH_OK();

@@ -331,7 +331,7 @@ int launch_wgrad_t(const float* A, int64_t lda, const float* H, const float* B, 
             if (B) GCA_TRY(set_smem(k_wgrad_stream<R, true>, smem, true));
             else GCA_TRY(set_smem(k_wgrad_stream<R, false>, smem, true));
             for (int col0 = 0; col0 < d; col0 += 256) {
-                ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st);
+                ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st, "mma");
                 if (B)
                     GCA_CUDA(launch_pdl(k_wgrad_stream<R, true>, dim3(grid), dim3(256), smem, st, A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d, col0));
                 else
@@ -361,7 +361,7 @@ int launch_wgrad_t(const float* A, int64_t lda, const float* H, const float* B, 
         if (smem > 200 * 1024) return GCA_ERR_UNSUPPORTED;
         GCA_TRY(set_smem(k_wgrad<R>, smem));
         {
-            ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st);
+            ProfScope ps(slot == 0 ? "wgrad_up" : "wgrad_down", st, "ffma");
             k_wgrad<R><<<grid, warps * 32, smem, st>>>(A, lda, H, B, ldb, partG, partCol, partDot, header, slot, n, d,
                                                         col0, dsub, nchunks, RS);
         }
