@@ -28,6 +28,20 @@ _f = C.c_void_p       # device pointers travel as integers
 _i32, _i64, _sz = C.c_int32, C.c_int64, C.c_size_t
 
 
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class Push(C.Structure):
+    """gca_push: peer-mapped destinations that receive the rows a producing phase writes (include/gca.h)."""
+    _fields_ = [("count", _i32), ("reserved", _i32), ("dst", C.c_void_p * MAX_PEERS)]
+
+
+class PeerSync(C.Structure):
+    """gca_peer_sync: the flag arrays of all GPUs of the group + the local sequence counter."""
+    _fields_ = [("world", _i32), ("rank", _i32), ("flags", C.c_void_p * MAX_PEERS), ("seq", C.c_void_p)]
+
+
 class GraphView(C.Structure):
     _fields_ = [("N", _i32), ("row_begin", _i32), ("row_end", _i32), ("normalize", _i32),
                 ("capacity", _i64), ("rowptr", _f), ("colidx", _f), ("rowptr_t", _f), ("colidx_t", _f), ("dis", _f)]
@@ -47,14 +61,14 @@ SIGNATURES = {
     "gca_graph_edge_coef": (C.c_int, [_f, _f, _f]),
     "gca_hub_scratch_bytes": (_sz, [_f]),
     "gca_propagate": (C.c_int, [_f, C.c_int, _f, _i64, _f, _i64, _i32, _f]),
-    "gca_fwd_project": (C.c_int, [_f, _f, _i64, _f, _f, _i32, _i32, _f]),
-    "gca_fwd_hop1": (C.c_int, [_f, _f, _f, C.c_int, _f, _f, _f, _i32, _f]),
+    "gca_fwd_project": (C.c_int, [_f, _f, _i64, _f, _f, C.POINTER(Push), _i32, _i32, _f]),
+    "gca_fwd_hop1": (C.c_int, [_f, _f, _f, C.c_int, _f, _f, _f, C.POINTER(Push), _i32, _f]),
     "gca_fwd_hop2_up": (C.c_int, [_f, _f, _f, _i64, _f, _f, _f, C.c_int, _f, _f, _i64, _f, _i32, _i32, _f]),
     "gca_bwd_scratch_bytes": (_sz, [_i32, _i32]),
-    "gca_bwd_up": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f]),
-    "gca_bwd_up_project": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _i32, _i32, _f]),
+    "gca_bwd_up": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, _f, C.POINTER(Push), _i32, _i32, _f]),
+    "gca_bwd_up_project": (C.c_int, [_f, _f, _i64, _f, _f, _f, _f, C.POINTER(Push), _i32, _i32, _f]),
     "gca_bwd_up_wgrad": (C.c_int, [_f, _f, _i64, _f, _f, _i32, _i32, _f]),
-    "gca_bwd_hop2": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _f, _i32, _f]),
+    "gca_bwd_hop2": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _f, C.POINTER(Push), _i32, _f]),
     "gca_bwd_hop1_down": (C.c_int, [_f, _f, _f, _i64, _f, _i64, _f, _f, C.c_int, _f, _f, _i64, _f, _f, _i32, _i32, _f]),
     "gca_bwd_finalize": (C.c_int, [_f, _f, _f, _f, C.c_int, _f, _f, _f, _f, _f, _i32, _i32, _f]),
     "gca_forward_workspace_bytes": (_sz, [_f, _i32, _i32]),
@@ -62,6 +76,14 @@ SIGNATURES = {
     "gca_backward_workspace_bytes": (_sz, [_f, _i32, _i32]),
     "gca_backward": (C.c_int, [_f, _f, _i64, _f, _i64, _f, _f, _f, _f, _f, _f, _f, C.c_int, C.c_int, _f,
                                _f, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f]),
+    "gca_peer_barrier": (C.c_int, [C.POINTER(PeerSync), _f]),
+    "gca_peer_allreduce": (C.c_int, [C.POINTER(PeerSync), C.POINTER(Push), _f, _f, _i32, _f]),
+    "gca_push_rows": (C.c_int, [_f, _i64, C.POINTER(Push), _f]),
+    "gca_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p)]),
+    "gca_peer_free": (C.c_int, [_f]),
+    "gca_peer_export": (C.c_int, [_f, C.c_char_p]),
+    "gca_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "gca_peer_close": (C.c_int, [_f]),
     "gca_launch_count": (_i64, []),
     "gca_profile_enable": (C.c_int, [C.c_int]),
     "gca_profile_report": (C.c_int, [C.c_char_p, _sz]),

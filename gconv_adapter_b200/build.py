@@ -85,6 +85,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for old in glob.glob(os.path.join(LIB_DIR, "libgca*.so")):      # one binary per tree: drop builds of older sources
         if os.path.abspath(old) != os.path.abspath(out):
             os.remove(old)
+    for old in glob.glob(os.path.join(ROOT, "build", "obj", "*")):  # ... and their objects
+        if os.path.abspath(old) != os.path.abspath(obj_dir):
+            shutil.rmtree(old, ignore_errors=True)
     return out
 
 

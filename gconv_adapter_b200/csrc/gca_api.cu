@@ -17,13 +17,15 @@ inline bool hub_scratch_ok(const gca_graph* g, const void* hub_scratch) {
 
 // K1 through the streaming family when the shape allows, else the register-fed kernels.
 int project_any(int r, bool w_is_rd, const float* A, int64_t lda, const float* W, const float* rowscale, const float* scalar,
-                float* out, int n, int d, cudaStream_t st) {
+                float* out, int n, int d, const gca_push* push, cudaStream_t st) {
     DenseStreamArgs a{};
-    a.A = A; a.lda = lda; a.W = W; a.w_is_rd = w_is_rd; a.rowscale = rowscale; a.scalar = scalar; a.out = out;
+    a.A = A; a.lda = lda; a.W = W; a.w_is_rd = w_is_rd; a.rowscale = rowscale; a.scalar = scalar; a.out = out; a.push = push;
     a.n = n; a.d = d; a.prof_name = w_is_rd ? "project_fwd" : "project_bwd";
     const int s = launch_dense_stream(r, a, st);
     if (s != GCA_ERR_UNSUPPORTED) return s;
-    return launch_project(r, w_is_rd, A, lda, W, rowscale, scalar, out, n, d, st);
+    // register-fed kernels have no fused push: copy the finished shard to the peers
+    GCA_TRY(launch_project(r, w_is_rd, A, lda, W, rowscale, scalar, out, n, d, st));
+    return launch_push_rows(out, (size_t)n * r, push, st);
 }
 
 // K4 through the streaming family when the shape allows, else the register-fed kernels.
@@ -39,23 +41,23 @@ int wgrad_any(int r, const float* A, int64_t lda, const float* H, const float* B
 }  // namespace
 
 extern "C" int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, const float* Wd, float* Pp_local,
-                               int32_t d, int32_t r, gca_stream_t stream) {
+                               const gca_push* push, int32_t d, int32_t r, gca_stream_t stream) {
     if (!g || !X || !Wd || !Pp_local || ldx < d) return GCA_ERR_INVALID_ARG;
     if (!shape_ok(d, r) || (ldx % 4) != 0) return GCA_ERR_UNSUPPORTED;
     const int n = g->row_end - g->row_begin;
     if (n == 0) return GCA_OK;
-    return project_any(r, true, X, ldx, Wd, g->dis, nullptr, Pp_local, n, d, static_cast<cudaStream_t>(stream));
+    return project_any(r, true, X, ldx, Wd, g->dis, nullptr, Pp_local, n, d, push, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gca_fwd_hop1(const gca_graph* g, const float* Pp_full, const float* bd, int act, float* Zp_local,
-                            float* H1_local, void* hub_scratch, int32_t r, gca_stream_t stream) {
+                            float* H1_local, void* hub_scratch, const gca_push* push, int32_t r, gca_stream_t stream) {
     if (!g || !Pp_full || !bd || !Zp_local) return GCA_ERR_INVALID_ARG;
     if (act < GCA_ACT_NONE || act > GCA_ACT_SILU) return GCA_ERR_INVALID_ARG;
     if (act == GCA_ACT_SILU && !H1_local) return GCA_ERR_INVALID_ARG;
     if (!hub_scratch_ok(g, hub_scratch)) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
     return launch_hop(r, false, csr_of(g, false, hub_scratch), Pp_full, bd, act, nullptr, nullptr, Zp_local, H1_local, nullptr,
-                      nullptr, n, static_cast<cudaStream_t>(stream), 0, nullptr);
+                      nullptr, n, static_cast<cudaStream_t>(stream), 0, nullptr, push);
 }
 
 extern "C" int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full, const float* X, int64_t ldx, const float* Wu,
@@ -76,7 +78,7 @@ extern "C" size_t gca_bwd_scratch_bytes(int32_t d, int32_t r) {
 }
 
 extern "C" int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, const float* Wu,
-                          const float* scalar, float* gH2p_local, void* scratch, int32_t d, int32_t r,
+                          const float* scalar, float* gH2p_local, void* scratch, const gca_push* push, int32_t d, int32_t r,
                           gca_stream_t stream) {
     if (!g || !gY || !H2_local || !Wu || !gH2p_local || !scratch || ldg < d) return GCA_ERR_INVALID_ARG;
     if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
@@ -88,18 +90,18 @@ extern "C" int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, cons
     if (n == 0) return GCA_OK;
     // one pass over gY for both the projection and the weight gradient (r = 16) ...
     DenseStreamArgs a{};
-    a.A = gY; a.lda = ldg; a.W = Wu; a.w_is_rd = false; a.rowscale = g->dis; a.scalar = scalar; a.out = gH2p_local;
+    a.A = gY; a.lda = ldg; a.W = Wu; a.w_is_rd = false; a.rowscale = g->dis; a.scalar = scalar; a.out = gH2p_local; a.push = push;
     a.H = H2_local; a.partG = S.gu; a.partCol = S.col; a.header = S.header; a.slot = 0; a.n = n; a.d = d;
     a.prof_name = "bwd_up";
     const int s = launch_dense_stream(r, a, st);
     if (s != GCA_ERR_UNSUPPORTED) return s;
     // ... else two passes
-    GCA_TRY(project_any(r, false, gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, st));
+    GCA_TRY(project_any(r, false, gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, push, st));
     return wgrad_any(r, gY, ldg, H2_local, nullptr, 0, S.gu, S.col, nullptr, S.header, 0, n, d, st);
 }
 
 extern "C" int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t ldg, const float* Wu, const float* scalar,
-                                  float* gH2p_local, void* scratch, int32_t d, int32_t r, gca_stream_t stream) {
+                                  float* gH2p_local, void* scratch, const gca_push* push, int32_t d, int32_t r, gca_stream_t stream) {
     if (!g || !gY || !Wu || !gH2p_local || !scratch || ldg < d) return GCA_ERR_INVALID_ARG;
     if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
@@ -108,7 +110,7 @@ extern "C" int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t l
     const Scratch S = scratch_ptrs(scratch, d, r);
     GCA_CUDA(cudaMemsetAsync(S.header, 0, 256, st));
     if (n == 0) return GCA_OK;
-    return project_any(r, false, gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, st);
+    return project_any(r, false, gY, ldg, Wu, g->dis, scalar, gH2p_local, n, d, push, st);
 }
 
 extern "C" int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, void* scratch,
@@ -122,7 +124,8 @@ extern "C" int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg
 }
 
 extern "C" int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full, const float* Zp_local, const float* H1_local,
-                            int act, float* gH1p_local, void* scratch, void* hub_scratch, int32_t r, gca_stream_t stream) {
+                            int act, float* gH1p_local, void* scratch, void* hub_scratch, const gca_push* push, int32_t r,
+                            gca_stream_t stream) {
     if (!g || !gH2p_full || !gH1p_local || !scratch) return GCA_ERR_INVALID_ARG;
     if (act < GCA_ACT_NONE || act > GCA_ACT_SILU) return GCA_ERR_INVALID_ARG;
     if ((act == GCA_ACT_RELU && !Zp_local) || (act == GCA_ACT_SILU && !H1_local)) return GCA_ERR_INVALID_ARG;
@@ -130,7 +133,7 @@ extern "C" int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full, const fl
     const int n = g->row_end - g->row_begin;
     const Scratch S = scratch_ptrs(scratch, 4, r);      // header / bd offsets do not depend on d
     return launch_hop(r, true, csr_of(g, true, hub_scratch), gH2p_full, nullptr, act, Zp_local, H1_local, gH1p_local, nullptr,
-                      S.bd, S.header, n, static_cast<cudaStream_t>(stream), 0, nullptr);
+                      S.bd, S.header, n, static_cast<cudaStream_t>(stream), 0, nullptr, push);
 }
 
 extern "C" int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full, const float* X, int64_t ldx,
@@ -183,8 +186,8 @@ extern "C" int gca_forward(const gca_graph* g, const float* X, int64_t ldx, cons
     char* b = static_cast<char*>(workspace);
     float* Pp = reinterpret_cast<float*>(b);
     void* hub = hub_scratch_bytes(g) ? b + rw_bytes(g->N, r) : nullptr;
-    GCA_TRY(gca_fwd_project(g, X, ldx, Wd, Pp, d, r, stream));
-    GCA_TRY(gca_fwd_hop1(g, Pp, bd, act, Zp_save, H1_save, hub, r, stream));
+    GCA_TRY(gca_fwd_project(g, X, ldx, Wd, Pp, nullptr, d, r, stream));
+    GCA_TRY(gca_fwd_hop1(g, Pp, bd, act, Zp_save, H1_save, hub, nullptr, r, stream));
     return gca_fwd_hop2_up(g, Zp_save, X, ldx, Wu, bu, scalar, skip, H2_save, Y, ldy, hub, d, r, stream);
 }
 
@@ -208,8 +211,8 @@ extern "C" int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, co
     float* gP = reinterpret_cast<float*>(b + 2 * rw);
     void* scratch = b + 3 * rw;
     void* hub = hub_scratch_bytes(g) ? b + 3 * rw + gca_bwd_scratch_bytes(d, r) : nullptr;
-    GCA_TRY(gca_bwd_up(g, gY, ldg, H2_save, Wu, scalar, gH2p, scratch, d, r, stream));
-    GCA_TRY(gca_bwd_hop2(g, gH2p, Zp_save, H1_save, act, gH1p, scratch, hub, r, stream));
+    GCA_TRY(gca_bwd_up(g, gY, ldg, H2_save, Wu, scalar, gH2p, scratch, nullptr, d, r, stream));
+    GCA_TRY(gca_bwd_hop2(g, gH2p, Zp_save, H1_save, act, gH1p, scratch, hub, nullptr, r, stream));
     GCA_TRY(gca_bwd_hop1_down(g, gH1p, X, ldx, gY, ldg, Wd, scalar, skip, gP, gX, ldgx, scratch, hub, d, r, stream));
     return gca_bwd_finalize(scratch, Wu, bu, scalar, skip, gWd, gbd, gWu, gbu, gscalar, d, r, stream);
 }

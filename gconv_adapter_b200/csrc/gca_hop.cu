@@ -48,7 +48,7 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
       const float* __restrict__ F, const float* __restrict__ bias, int act,
       const float* __restrict__ Zp_saved, const float* __restrict__ H1_saved,
       float* __restrict__ out, float* __restrict__ H1_out, float* __restrict__ part_bd, int* header, int n,
-      const int* __restrict__ hubitem, const float* __restrict__ hub_part, int plain) {
+      const int* __restrict__ hubitem, const float* __restrict__ hub_part, int plain, const gca_push push) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPG, grp = lane / LPG;
@@ -73,7 +73,9 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
             float4 h = make_float4(fmaf(di, acc.x, b4.x), fmaf(di, acc.y, b4.y), fmaf(di, acc.z, b4.z), fmaf(di, acc.w, b4.w));
             if (H1_out) *reinterpret_cast<float4*>(H1_out + o) = h;
             h = make_float4(act_apply(h.x, act), act_apply(h.y, act), act_apply(h.z, act), act_apply(h.w, act));
-            *reinterpret_cast<float4*>(out + o) = f4_scale(h, di);
+            const float4 zo = f4_scale(h, di);
+            *reinterpret_cast<float4*>(out + o) = zo;
+            for (int hp = 0; hp < push.count; ++hp) *reinterpret_cast<float4*>(push.dst[hp] + o) = zo;   // peers' gathered buffers
         } else {
             float4 g = f4_scale(acc, di);
             if (act == GCA_ACT_RELU) {
@@ -84,7 +86,9 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
                 g = make_float4(g.x * silu_grad(h.x), g.y * silu_grad(h.y), g.z * silu_grad(h.z), g.w * silu_grad(h.w));
             }
             gb = f4_add(gb, g);
-            *reinterpret_cast<float4*>(out + o) = f4_scale(g, di);
+            const float4 go = f4_scale(g, di);
+            *reinterpret_cast<float4*>(out + o) = go;
+            for (int hp = 0; hp < push.count; ++hp) *reinterpret_cast<float4*>(push.dst[hp] + o) = go;
         }
     }
     if (BWD) {
@@ -121,8 +125,11 @@ int launch_hub_partials_t(const Csr& c, const float* F, cudaStream_t st) {
 template <int R, bool BWD>
 int launch_hop_t(const Csr& c, const float* F, const float* bias, int act,
                  const float* Zp, const float* H1s, float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st,
-                 int plain, const char* prof_name) {
+                 int plain, const char* prof_name, const gca_push* push) {
     constexpr int GPW = 32 / (R / 4);
+    gca_push pv{};
+    if (push && !plain) pv = *push;
+    if (pv.count < 0 || pv.count > GCA_MAX_PEERS) return GCA_ERR_INVALID_ARG;
     GCA_TRY(launch_hub_partials_t<R>(c, F, st));
     const int* rowptr = c.rowptr; const int* colidx = c.colidx; const float* dis = c.dis;
     int grid = (n + 8 * GPW - 1) / (8 * GPW);
@@ -138,7 +145,7 @@ int launch_hop_t(const Csr& c, const float* F, const float* bias, int act,
     if (grid < 1) grid = 1;
     {
         ProfScope ps(prof_name ? prof_name : (BWD ? "hop_bwd" : "hop_fwd"), st);
-        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, c.hubitem, c.hub_part, plain));
+        GCA_CUDA(launch_pdl(k_hop<R, BWD>, dim3(grid), dim3(256), 0, st, rowptr, colidx, dis, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, c.hubitem, c.hub_part, plain, pv));
     }
     GCA_LAUNCH_OK();
     return GCA_OK;
@@ -147,9 +154,10 @@ int launch_hop_t(const Csr& c, const float* F, const float* bias, int act,
 }  // namespace
 
 int launch_hop(int r, bool bwd, const Csr& c, const float* F, const float* bias, int act, const float* Zp, const float* H1s,
-               float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st, int plain, const char* prof_name) {
-    if (bwd) { GCA_DISPATCH_R(r, (launch_hop_t<R_, true>(c, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, st, plain, prof_name))); }
-    GCA_DISPATCH_R(r, (launch_hop_t<R_, false>(c, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, st, plain, prof_name)));
+               float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st, int plain, const char* prof_name,
+               const gca_push* push) {
+    if (bwd) { GCA_DISPATCH_R(r, (launch_hop_t<R_, true>(c, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, st, plain, prof_name, push))); }
+    GCA_DISPATCH_R(r, (launch_hop_t<R_, false>(c, F, bias, act, Zp, H1s, out, H1o, part_bd, header, n, st, plain, prof_name, push)));
 }
 int launch_hub_partials(int r, const Csr& c, const float* F, cudaStream_t st) {
     GCA_DISPATCH_R(r, (launch_hub_partials_t<R_>(c, F, st)));

@@ -93,7 +93,10 @@ int launch_project_tc(int r, bool w_is_rd, const float* A, int64_t lda, const fl
                       const float* scalar, float* out, int n, int d, cudaStream_t st);
 // K2: r-wide hop (forward: bias + act ; backward: act' + bias-gradient partials ; plain: just the hop)
 int launch_hop(int r, bool bwd, const Csr& c, const float* F, const float* bias, int act, const float* Zp, const float* H1s,
-               float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st, int plain, const char* prof_name);
+               float* out, float* H1o, float* part_bd, int* header, int n, cudaStream_t st, int plain, const char* prof_name,
+               const gca_push* push = nullptr);
+// copy a finished local shard to the peers (producers without a fused push)
+int launch_push_rows(const float* src, size_t nfloats, const gca_push* push, cudaStream_t st);
 // K3: hop + expansion  Out = alpha (H W + bias) + beta Resid   (w_is_dr: W stored [d, r], else [r, d])
 int launch_hop_expand(int r, bool w_is_dr, const Csr& c, const float* F, const float* W, const float* bias, const float* resid,
                       int64_t ldr, const float* scalar, int alpha_is_scalar, int use_resid, float* Hout, float* Out, int64_t ldo,
@@ -108,6 +111,7 @@ struct DenseStreamArgs {
     const float* B; int64_t ldb;                 // second stream for <A, B> (wgrad only), or null
     // projection (null W = no projection)
     const float* W; bool w_is_rd; const float* rowscale; const float* scalar; float* out;
+    const gca_push* push;                        // peers that receive every output row as well (or null)
     // weight gradient (null H = none)
     const float* H; float* partG; float* partCol; float* partDot; int* header; int slot;
     int n, d;

@@ -60,6 +60,7 @@ struct StreamParams {
     float* partG; float* partCol; float* partDot; int* header; int slot;
     int n, d, nb, stages;
     uint32_t stage_bytes, b_off, h_off, sc_off, tx_bytes, red_off, bar_off;
+    gca_push push;   // peers that receive every projected row as well (count = 0: none)
 };
 
 // byte offset of the 16-byte chunk `chunk` of row `row` inside a box of 128-byte rows with the 128-byte swizzle
@@ -343,8 +344,15 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int slot = idx >> 5, g2 = (idx & 31) >> 2, t2 = idx & 3;
                 const int mt = slot / NT, nt = slot - mt * NT;
                 const int row_a = (t0 + k) * kSRows + 16 * mt + (g2 >> 1) + 4 * (g2 & 1);
-                if (row_a < p.n) *reinterpret_cast<float2*>(p.out + (size_t)row_a * R + nt * 8 + 2 * t2) = make_float2(v.x, v.y);
-                if (row_a + 8 < p.n) *reinterpret_cast<float2*>(p.out + (size_t)(row_a + 8) * R + nt * 8 + 2 * t2) = make_float2(v.z, v.w);
+                const size_t oa = (size_t)row_a * R + nt * 8 + 2 * t2, ob = oa + 8 * R;
+                if (row_a < p.n) {
+                    *reinterpret_cast<float2*>(p.out + oa) = make_float2(v.x, v.y);
+                    for (int hp = 0; hp < p.push.count; ++hp) *reinterpret_cast<float2*>(p.push.dst[hp] + oa) = make_float2(v.x, v.y);
+                }
+                if (row_a + 8 < p.n) {
+                    *reinterpret_cast<float2*>(p.out + ob) = make_float2(v.z, v.w);
+                    for (int hp = 0; hp < p.push.count; ++hp) *reinterpret_cast<float2*>(p.push.dst[hp] + ob) = make_float2(v.z, v.w);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(red_free(rbuf));
@@ -575,6 +583,10 @@ int launch_dense_stream_t(const DenseStreamArgs& a, cudaStream_t st) {
         p.W = a.W; p.rowscale = a.rowscale; p.scalar = a.scalar; p.out = a.out;
         p.partG = a.partG; p.partCol = a.partCol; p.partDot = a.partDot; p.header = a.header; p.slot = a.slot;
         p.n = a.n; p.d = a.d; p.nb = a.d / 32;
+        if (proj && a.push) {
+            if (a.push->count < 0 || a.push->count > GCA_MAX_PEERS) return GCA_ERR_INVALID_ARG;
+            p.push = *a.push;
+        }
         const uint32_t a_bytes = (uint32_t)p.nb * kSBox;
         const uint32_t h_bytes = wgrad ? (uint32_t)(kSRows * R * 4) : 0u;
         p.b_off = dot ? a_bytes : 0u;

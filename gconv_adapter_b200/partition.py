@@ -5,11 +5,20 @@ scale-out the north star asks for: node rows are split into contiguous blocks, e
 rows of X / Y / all gradients and the CSR rows (targets) of its block, and only the r-wide operand of
 each sparse hop crosses NVLink:
 
-    forward : P' -> all-gather -> Z' -> all-gather -> Y            (2 gathers of [N, r] fp32)
-    backward: gH2' -> all-gather -> gH1' -> all-gather -> gX, then one all-reduce of the
+    forward : P' -> gather -> Z' -> gather -> Y                    (2 gathers of [N, r] fp32)
+    backward: gH2' -> gather -> gH1' -> gather -> gX, then one all-reduce of the
               2 d r + d + r + 1 parameter-gradient floats.
 
 Communication therefore scales with the adapter rank r, never with the hidden width d.
+
+Two exchange mechanisms (``comm``):
+
+* ``PeerMemoryComm`` (default on CUDA): the kernel that PRODUCES an r-wide operand stores every finished row straight
+  into its peers' gathered buffers over NVLink (``gca_push``, peer memory mapped with CUDA IPC), so the "gather" left
+  between two phases is a one-warp barrier kernel, and the gradient all-reduce is one kernel over peer memory with a
+  fixed rank order.  No NCCL call inside a step: the whole forward + backward can be captured in a CUDA graph.
+* ``CollectiveComm``: ``torch.distributed`` all-gather / all-reduce (NCCL or gloo) - the portable path, used by the CPU
+  tests of the orchestration and as a fallback when peer mapping is unavailable (GCA_PARTITION_COMM=nccl).
 
 Shards have equal size S = ceil(N / world) (the last ranks may own fewer or zero real rows), so the
 gathered buffer is [world * S, r] and a global node id is directly its row in that buffer.
@@ -20,6 +29,8 @@ can be exercised on CPU with gloo by the tests, which inject their own checker b
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -29,6 +40,11 @@ import torch.nn as nn
 from . import _cabi
 from .finetune.gconv_adapter import GConvAdapter
 from .graphs.csr import GraphStructure
+
+
+# Test hook: when True, the forward keeps this rank's rows of Z' (the ReLU decisions) in LAST_SAVED["zp"].
+DEBUG_KEEP_SAVED = False
+LAST_SAVED: dict = {}
 
 
 def shard_size(num_nodes: int, world: int) -> int:
@@ -56,22 +72,27 @@ class CudaPhases:
     def _stream(t: torch.Tensor) -> int:
         return torch.cuda.current_stream(t.device).cuda_stream
 
+    @staticmethod
+    def _push(push):
+        return C.byref(push) if push is not None else None
+
     def build_graph(self, edge_index, num_nodes, normalize, lo, hi):
         return GraphStructure(edge_index, num_nodes, normalize, lo, hi)
-
-    def fwd_project(self, g, x, wd, out_local):
-        d, r = x.shape[1], wd.shape[0]
-        _cabi.check(self.lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out_local.data_ptr(),
-                                             d, r, self._stream(x)), "gca_fwd_project")
 
     def hub_scratch(self, g, device):
         """Per-call scratch for the partial sums of hub rows (None when the graph has no row longer than 512)."""
         nbytes = self.lib.gca_hub_scratch_bytes(g.handle)
         return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes else None
 
-    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local, hub=None):
+    def fwd_project(self, g, x, wd, out_local, push=None):
+        d, r = x.shape[1], wd.shape[0]
+        _cabi.check(self.lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out_local.data_ptr(),
+                                             self._push(push), d, r, self._stream(x)), "gca_fwd_project")
+
+    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local, hub=None, push=None):
         _cabi.check(self.lib.gca_fwd_hop1(g.handle, p_full.data_ptr(), bd.data_ptr(), act, z_local.data_ptr(),
-                                          _ptr(h1_local), _ptr(hub), bd.shape[0], self._stream(p_full)), "gca_fwd_hop1")
+                                          _ptr(h1_local), _ptr(hub), self._push(push), bd.shape[0], self._stream(p_full)),
+                    "gca_fwd_hop1")
 
     def fwd_hop2_up(self, g, z_full, x, wu, bu, scalar, skip, h2_local, y, hub=None):
         d, r = wu.shape
@@ -82,27 +103,17 @@ class CudaPhases:
     def bwd_scratch(self, d, r, device):
         return torch.empty(self.lib.gca_bwd_scratch_bytes(d, r), dtype=torch.uint8, device=device)
 
-    def bwd_up(self, g, gy, h2_local, wu, scalar, gh2_local, scratch):
+    def bwd_up(self, g, gy, h2_local, wu, scalar, gh2_local, scratch, push=None):
         d, r = wu.shape
         _cabi.check(self.lib.gca_bwd_up(g.handle, gy.data_ptr(), gy.stride(0), h2_local.data_ptr(), wu.data_ptr(),
-                                        _ptr(scalar), gh2_local.data_ptr(), scratch.data_ptr(), d, r,
+                                        _ptr(scalar), gh2_local.data_ptr(), scratch.data_ptr(), self._push(push), d, r,
                                         self._stream(gy)), "gca_bwd_up")
 
-    def bwd_up_project(self, g, gy, wu, scalar, gh2_local, scratch):
-        d, r = wu.shape
-        _cabi.check(self.lib.gca_bwd_up_project(g.handle, gy.data_ptr(), gy.stride(0), wu.data_ptr(), _ptr(scalar),
-                                                gh2_local.data_ptr(), scratch.data_ptr(), d, r, self._stream(gy)),
-                    "gca_bwd_up_project")
-
-    def bwd_up_wgrad(self, g, gy, h2_local, scratch, d, r):
-        _cabi.check(self.lib.gca_bwd_up_wgrad(g.handle, gy.data_ptr(), gy.stride(0), h2_local.data_ptr(),
-                                              scratch.data_ptr(), d, r, self._stream(gy)), "gca_bwd_up_wgrad")
-
-    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch, hub=None):
+    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch, hub=None, push=None):
         r = gh2_full.shape[1]
         _cabi.check(self.lib.gca_bwd_hop2(g.handle, gh2_full.data_ptr(), z_local.data_ptr(), _ptr(h1_local), act,
-                                          gh1_local.data_ptr(), scratch.data_ptr(), _ptr(hub), r, self._stream(gh2_full)),
-                    "gca_bwd_hop2")
+                                          gh1_local.data_ptr(), scratch.data_ptr(), _ptr(hub), self._push(push), r,
+                                          self._stream(gh2_full)), "gca_bwd_hop2")
 
     def bwd_hop1_down(self, g, gh1_full, x, gy, wd, scalar, skip, gp_local, gx, scratch, hub=None):
         r, d = wd.shape
@@ -118,17 +129,74 @@ class CudaPhases:
                                               _ptr(g_s), d, r, self._stream(wu)), "gca_bwd_finalize")
 
 
-def _all_gather_rows(full: torch.Tensor, lo: int, s: int, group, async_op: bool = False):
-    """In-place all-gather: every rank contributes rows [rank*S, (rank+1)*S) of ``full``."""
-    if dist.get_world_size(group) == 1:
+# ---------------------------------------------------------------------------------------------------------------
+# exchange mechanisms
+# ---------------------------------------------------------------------------------------------------------------
+GATHERED = ("p", "z", "gh2", "gh1")      # the four r-wide operands that every rank needs in full
+
+
+class CollectiveComm:
+    """torch.distributed collectives (NCCL / gloo): every gather is an in-place all_gather_into_tensor."""
+
+    fused_push = False
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def buffers(self, rows: int, r: int, device, which):
+        return {k: torch.empty((rows, r), dtype=torch.float32, device=device) for k in which}
+
+    def push(self, name, lo, r):
         return None
-    return dist.all_gather_into_tensor(full, full[lo:lo + s], group=group, async_op=async_op)
+
+    def gather(self, full: torch.Tensor, lo: int, s: int) -> None:
+        if self.world > 1:
+            dist.all_gather_into_tensor(full, full[lo:lo + s], group=self.group)
+
+    def allreduce_(self, flat: torch.Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class PeerMemoryComm:
+    """NVLink peer memory: gathered buffers live in a symmetric arena (gconv_adapter_b200/peer.py); producers push
+    their rows into the peers' copies while they compute, a gather is only the barrier kernel."""
+
+    fused_push = True
+
+    def __init__(self, num_nodes: int, d: int, r: int, group=None, device=None):
+        from .peer import PeerGroup
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows = self.world * shard_size(num_nodes, self.world)
+        self.r = r
+        self.buf_bytes = 4 * self.rows * r
+        self.pg = PeerGroup([self.buf_bytes] * len(GATHERED), slot_floats=2 * d * r + d + r + 1, group=group, device=device)
+        self._views = {k: self.pg.region(i, self.buf_bytes).view(torch.float32).view(self.rows, r) for i, k in enumerate(GATHERED)}
+
+    def buffers(self, rows: int, r: int, device, which):
+        assert rows == self.rows and r == self.r
+        return {k: self._views[k] for k in which}
+
+    def push(self, name, lo, r):
+        return self.pg.push_to_peers(GATHERED.index(name), 4 * lo * r)
+
+    def gather(self, full: torch.Tensor, lo: int, s: int) -> None:
+        self.pg.barrier()
+
+    def allreduce_(self, flat: torch.Tensor) -> None:
+        self.pg.allreduce_(flat)
+
+    def close(self) -> None:
+        self._views = {}
+        self.pg.close()
 
 
 class _PartitionedFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w_down, b_down, w_up, b_up, scalar, graph, act, skip, num_nodes, group, backend):
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    def forward(ctx, x, w_down, b_down, w_up, b_up, scalar, graph, act, skip, num_nodes, comm, backend):
+        world, rank = comm.world, comm.rank
         s = shard_size(num_nodes, world)
         lo = rank * s
         n, d = x.shape
@@ -136,45 +204,50 @@ class _PartitionedFunction(torch.autograd.Function):
         dev = x.device
         w_down, b_down, w_up, b_up = (t.contiguous() for t in (w_down, b_down, w_up, b_up))
         # padded rows (beyond N) of the gathered buffers are never referenced by any neighbour id, so the
-        # buffers need no initialisation: every real row is written by its owner's kernel or by the all-gather
-        p_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
-        z_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
+        # buffers need no initialisation: every real row is written by its owner's kernel or arrives from a peer
+        bufs = comm.buffers(world * s, r, dev, ("p", "z"))
+        p_full, z_full = bufs["p"], bufs["z"]
         h2 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
         h1 = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev) if act == _cabi.ACT["silu"] else None
         y = torch.empty((n, d), dtype=torch.float32, device=dev)
         hub = backend.hub_scratch(graph, dev) if hasattr(backend, "hub_scratch") else None
         if n > 0:
-            backend.fwd_project(graph, x, w_down, p_full[lo:lo + n])
-        _all_gather_rows(p_full, lo, s, group)
+            backend.fwd_project(graph, x, w_down, p_full[lo:lo + n], push=comm.push("p", lo, r))
+        comm.gather(p_full, lo, s)
         if n > 0:
-            backend.fwd_hop1(graph, p_full, b_down, act, z_full[lo:lo + n], h1, hub)
-        _all_gather_rows(z_full, lo, s, group)
+            backend.fwd_hop1(graph, p_full, b_down, act, z_full[lo:lo + n], h1, hub, push=comm.push("z", lo, r))
+        comm.gather(z_full, lo, s)
         if n > 0:
             backend.fwd_hop2_up(graph, z_full, x, w_up, b_up, scalar, skip, h2, y, hub)
-        ctx.graph, ctx.act, ctx.skip, ctx.group, ctx.backend = graph, act, skip, group, backend
+        ctx.graph, ctx.act, ctx.skip, ctx.comm, ctx.backend = graph, act, skip, comm, backend
         ctx.meta = (world, s, lo, n, d, r)
         ctx.has_scalar, ctx.has_h1 = scalar is not None, h1 is not None
-        saved = [x, w_down, w_up, b_up, z_full, h2]
+        # only this rank's rows of Z' are needed again (activation mask): with shared gathered buffers (peer arena)
+        # they are copied out, so that another forward may run before this backward
+        z_local = z_full[lo:lo + n].clone() if comm.fused_push else z_full[lo:lo + n]
+        saved = [x, w_down, w_up, b_up, z_local, h2]
         if scalar is not None:
             saved.append(scalar)
         if h1 is not None:
             saved.append(h1)
         ctx.save_for_backward(*saved)
+        if DEBUG_KEEP_SAVED:
+            LAST_SAVED["zp"] = z_local
         return y
 
     @staticmethod
     def backward(ctx, g_y):
         saved = list(ctx.saved_tensors)
-        x, w_down, w_up, b_up, z_full, h2 = saved[:6]
+        x, w_down, w_up, b_up, z_local, h2 = saved[:6]
         rest = saved[6:]
         scalar = rest.pop(0) if ctx.has_scalar else None
         h1 = rest.pop(0) if ctx.has_h1 else None
         world, s, lo, n, d, r = ctx.meta
-        backend, graph, group = ctx.backend, ctx.graph, ctx.group
+        backend, graph, comm = ctx.backend, ctx.graph, ctx.comm
         dev = x.device
         g_y = g_y.contiguous()
-        gh2_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
-        gh1_full = torch.empty((world * s, r), dtype=torch.float32, device=dev)
+        bufs = comm.buffers(world * s, r, dev, ("gh2", "gh1"))
+        gh2_full, gh1_full = bufs["gh2"], bufs["gh1"]
         gp = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
         need_x = ctx.needs_input_grad[0]
         g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
@@ -185,30 +258,20 @@ class _PartitionedFunction(torch.autograd.Function):
         g_bu = flat[2 * d * r:2 * d * r + d]
         g_bd = flat[2 * d * r + d:2 * d * r + d + r]
         g_s = flat[2 * d * r + d + r:]
-        # gH2' first, then its all-gather runs (on NCCL's stream) while the weight-gradient half of the same
-        # phase - which does not need remote rows - keeps this GPU busy
-        split = hasattr(backend, "bwd_up_project")
         hub = backend.hub_scratch(graph, dev) if hasattr(backend, "hub_scratch") else None
         if n > 0:
             scratch = backend.bwd_scratch(d, r, dev)
-            if split:
-                backend.bwd_up_project(graph, g_y, w_up, scalar, gh2_full[lo:lo + n], scratch)
-            else:
-                backend.bwd_up(graph, g_y, h2, w_up, scalar, gh2_full[lo:lo + n], scratch)
-        work = _all_gather_rows(gh2_full, lo, s, group, async_op=split)
-        if n > 0 and split:
-            backend.bwd_up_wgrad(graph, g_y, h2, scratch, d, r)
-        if work is not None:
-            work.wait()
+            # one pass over gY: gH2' (pushed to the peers row by row) together with the gWu / gbu partial sums
+            backend.bwd_up(graph, g_y, h2, w_up, scalar, gh2_full[lo:lo + n], scratch, push=comm.push("gh2", lo, r))
+        comm.gather(gh2_full, lo, s)
         if n > 0:
-            backend.bwd_hop2(graph, gh2_full, z_full[lo:lo + n], h1, ctx.act, gh1_full[lo:lo + n], scratch, hub)
-        _all_gather_rows(gh1_full, lo, s, group)
+            backend.bwd_hop2(graph, gh2_full, z_local, h1, ctx.act, gh1_full[lo:lo + n], scratch, hub, push=comm.push("gh1", lo, r))
+        comm.gather(gh1_full, lo, s)
         if n > 0:
             backend.bwd_hop1_down(graph, gh1_full, x, g_y, w_down, scalar, ctx.skip, gp, g_x, scratch, hub)
             backend.bwd_finalize(scratch, w_up, b_up, scalar, ctx.skip, g_wd, g_bd, g_wu, g_bu,
                                  g_s if scalar is not None else None)
-        if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        comm.allreduce_(flat)
         return (g_x, g_wd, g_bd, g_wu, g_bu, g_s.clone() if scalar is not None else None,
                 None, None, None, None, None, None)
 
@@ -235,14 +298,20 @@ class PartitionedGConvAdapter(GConvAdapter):
     and the FULL ``edge_index``; returns the same rows of the output.  Parameter gradients come back
     already summed over ranks, so every replica applies the same optimizer step.  Only the fused
     configuration (normalization='none') is partitioned; LayerNorm is row-local and works unchanged,
-    BatchNorm would need cross-rank statistics and is refused."""
+    BatchNorm would need cross-rank statistics and is refused.
 
-    def __init__(self, *args, process_group=None, phase_backend=None, **kwargs):
+    ``comm``: "peer" (NVLink peer memory, default for the CUDA backend), "collective" (torch.distributed
+    all-gather / all-reduce), or an object with the comm interface.  Every rank must make the same choice."""
+
+    def __init__(self, *args, process_group=None, phase_backend=None, comm=None, **kwargs):
         super().__init__(*args, **kwargs)
         if isinstance(self.normalization, nn.BatchNorm1d):
             raise ValueError("PartitionedGConvAdapter: batch_norm needs global batch statistics; use 'none' or 'layer_norm'")
         self.process_group = process_group
         self._backend = phase_backend
+        self._comm_choice = comm
+        self._comm = None
+        self._comm_key = None
         self._graphs: dict = {}
 
     def _graph(self, edge_index: torch.Tensor, num_nodes: int, lo: int, hi: int):
@@ -253,6 +322,30 @@ class PartitionedGConvAdapter(GConvAdapter):
             self._graphs.clear()
             self._graphs[key] = hit
         return hit[0]
+
+    def _get_comm(self, num_nodes: int, device):
+        choice = self._comm_choice
+        if choice is None:
+            choice = os.environ.get("GCA_PARTITION_COMM") or ("peer" if isinstance(self._backend, CudaPhases) else "collective")
+            if choice == "nccl":
+                choice = "collective"
+        if not isinstance(choice, str):
+            return choice
+        key = (choice, num_nodes, self.hidden_size, self.bottleneck_size)
+        if self._comm is None or self._comm_key != key:
+            self.close()
+            if choice == "peer" and dist.get_world_size(self.process_group) > 1:
+                self._comm = PeerMemoryComm(num_nodes, self.hidden_size, self.bottleneck_size, self.process_group, device)
+            else:
+                self._comm = CollectiveComm(self.process_group)
+            self._comm_key = key
+        return self._comm
+
+    def close(self) -> None:
+        """Unmap the peer arena (collective: call on every rank, before destroy_process_group)."""
+        if self._comm is not None and hasattr(self._comm, "close"):
+            self._comm.close()
+        self._comm, self._comm_key = None, None
 
     def forward(self, x_local: torch.Tensor, edge_index: torch.Tensor, num_nodes: int, edge_attr=None) -> torch.Tensor:
         if self._backend is None:
@@ -265,11 +358,12 @@ class PartitionedGConvAdapter(GConvAdapter):
         if self.hidden_size % 4 != 0 or self.bottleneck_size not in (8, 16, 32, 64):
             raise RuntimeError("PartitionedGConvAdapter needs hidden % 4 == 0 and bottleneck in {8,16,32,64}")
         graph = self._graph(edge_index, num_nodes, lo, hi)
+        comm = self._get_comm(num_nodes, x_local.device)
         x_local = x_local.contiguous()
         fused_scalar = self.scalar if self.normalization is None else None
         out = _PartitionedFunction.apply(x_local, self.conv_down.lin.weight, self.conv_down.bias,
                                          self.conv_up.lin.weight, self.conv_up.bias, fused_scalar, graph, self._act,
-                                         self.skip_connection, num_nodes, group, self._backend)
+                                         self.skip_connection, num_nodes, comm, self._backend)
         if isinstance(self.normalization, nn.LayerNorm):
             ln = self.normalization
             out = torch.nn.functional.layer_norm(out, ln.normalized_shape, _AllReduceGrad.apply(ln.weight, group),

@@ -58,6 +58,25 @@ typedef enum gca_status {
 
 typedef enum gca_act { GCA_ACT_NONE = 0, GCA_ACT_RELU = 1, GCA_ACT_SILU = 2 } gca_act;
 
+/* -------- multi-GPU (one process per GPU, rows partitioned) --------
+ * The r-wide operand of every sparse hop is needed in full on every GPU.  The phase that PRODUCES it takes a gca_push:
+ * peer-mapped device pointers (CUDA IPC, see gca_peer_*) to the caller's OWN rows inside each peer's gathered buffer,
+ * i.e. peer_full[h] + row_begin * r.  The producing kernel stores every finished row there as well (plain stores over
+ * NVLink / NVSwitch, overlapped with its own streaming), so no collective call sits between two phases - only
+ * gca_peer_barrier.  NULL or count = 0: single GPU, nothing is pushed. */
+#define GCA_MAX_PEERS 8
+#define GCA_IPC_HANDLE_BYTES 64
+typedef struct gca_push {
+    int32_t count;                    /* destinations, 0 .. GCA_MAX_PEERS */
+    int32_t reserved;
+    float*  dst[GCA_MAX_PEERS];
+} gca_push;
+typedef struct gca_peer_sync {
+    int32_t   world, rank;
+    uint32_t* flags[GCA_MAX_PEERS];   /* flags[h]: GPU h's flag array (world x uint32, zero-initialised), peer-mapped; [rank] = local */
+    uint32_t* seq;                    /* local device counter (zero-initialised), bumped by every barrier / all-reduce */
+} gca_peer_sync;
+
 /* -------- library -------- */
 int         gca_abi_version(void);
 const char* gca_status_string(int status);
@@ -120,12 +139,12 @@ int gca_propagate(const gca_graph* g, int transpose, const float* X_full /*[N,D]
  */
 /* conv_down.lin (d -> r) with the source-side D^-1/2 folded in: P'[i] = dis[i] * X[i] Wd^T */
 int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, const float* Wd /*[r,d]*/,
-                    float* Pp_local /*[n,r]*/, int32_t d, int32_t r, gca_stream_t stream);
+                    float* Pp_local /*[n,r]*/, const gca_push* push, int32_t d, int32_t r, gca_stream_t stream);
 /* conv_down.propagate + bias + act_fn, result pre-scaled for the next hop.
  * H1_local may be NULL unless act == GCA_ACT_SILU (backward needs the pre-activation). */
 int gca_fwd_hop1(const gca_graph* g, const float* Pp_full /*[N,r]*/, const float* bd /*[r]*/, int act,
-                 float* Zp_local /*[n,r]*/, float* H1_local /*[n,r] or NULL*/, void* hub_scratch, int32_t r,
-                 gca_stream_t stream);
+                 float* Zp_local /*[n,r]*/, float* H1_local /*[n,r] or NULL*/, void* hub_scratch, const gca_push* push,
+                 int32_t r, gca_stream_t stream);
 /* conv_up (propagate at width r, then lin r -> d, + bias) + skip + scalar.
  * scalar may be NULL (= 1).  H2_local is saved for the backward. */
 int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full /*[N,r]*/, const float* X, int64_t ldx,
@@ -139,18 +158,18 @@ size_t gca_bwd_scratch_bytes(int32_t d, int32_t r);
  * One pass over gY serves both (gca_stream.cu) when d % 32 == 0, d <= 256, r = 16. */
 int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local,
                const float* Wu, const float* scalar, float* gH2p_local /*[n,r]*/,
-               void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+               void* scratch, const gca_push* push, int32_t d, int32_t r, gca_stream_t stream);
 /* The two halves of gca_bwd_up as separate calls, so that a multi-GPU caller can start the all-gather of gH2'
  * between them (the weight-gradient half does not depend on it): _project clears the scratch header and writes
  * gH2', _wgrad accumulates the gWu / gbu partials. */
 int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t ldg, const float* Wu, const float* scalar,
-                       float* gH2p_local, void* scratch, int32_t d, int32_t r, gca_stream_t stream);
+                       float* gH2p_local, void* scratch, const gca_push* push, int32_t d, int32_t r, gca_stream_t stream);
 int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg, const float* H2_local, void* scratch,
                      int32_t d, int32_t r, gca_stream_t stream);
 /* gH1'[j] = dis[j] * act'(.) * dis[j] * sum_{i in out(j)} gH2'[i] ; partial sums for gbd */
 int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full /*[N,r]*/, const float* Zp_local,
                  const float* H1_local /*NULL unless silu*/, int act, float* gH1p_local /*[n,r]*/,
-                 void* scratch, void* hub_scratch, int32_t r, gca_stream_t stream);
+                 void* scratch, void* hub_scratch, const gca_push* push, int32_t r, gca_stream_t stream);
 /* gP[j] = dis[j] * sum_{i in out(j)} gH1'[i] ; gX = gP Wd [+ s * gY] ; partials for gWd = gP^T X
  * and for <gY, X> (needed by gscalar).  gX may be NULL (x does not require grad). */
 int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full /*[N,r]*/, const float* X, int64_t ldx,
@@ -177,6 +196,25 @@ int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, const float* 
                  int act, int skip, void* workspace,
                  float* gX, int64_t ldgx, float* gWd, float* gbd, float* gWu, float* gbu, float* gscalar,
                  int32_t d, int32_t r, gca_stream_t stream);
+
+/* -------- multi-GPU plumbing over peer memory --------
+ * gca_peer_barrier: returns (on the stream) once every GPU of the group has reached the same barrier in ITS stream: all
+ * rows pushed by kernels that precede it on any GPU are then visible locally.  Every rank issues the same sequence of
+ * barriers / all-reduces.  One warp; no host synchronisation; capturable in a CUDA graph.
+ * gca_peer_allreduce: out[i] = sum over ranks (in rank order: bitwise identical everywhere) of src[i]; slots->dst[h] is
+ * GPU h's slot array ([world][len] floats, peer-mapped), slots->count = world.
+ * gca_push_rows: copy nfloats (multiple of 4) floats of a finished local shard to the peers (for producers without a fused push).
+ * gca_peer_alloc / export / open / close / free: zero-initialised device memory that other processes of the node can map
+ * (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access); handles are GCA_IPC_HANDLE_BYTES bytes (host). */
+int gca_peer_barrier(const gca_peer_sync* sync, gca_stream_t stream);
+int gca_peer_allreduce(const gca_peer_sync* sync, const gca_push* slots, const float* src, float* out, int32_t len,
+                       gca_stream_t stream);
+int gca_push_rows(const float* src, int64_t nfloats, const gca_push* push, gca_stream_t stream);
+int gca_peer_alloc(size_t bytes, void** ptr /* host out */);
+int gca_peer_free(void* ptr);
+int gca_peer_export(void* ptr, void* handle64 /* host out */);
+int gca_peer_open(const void* handle64 /* host */, void** ptr /* host out */);
+int gca_peer_close(void* ptr);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t gca_launch_count(void);

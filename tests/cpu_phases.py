@@ -33,10 +33,10 @@ class CpuPhases:
     def build_graph(self, edge_index, num_nodes, normalize, lo, hi):
         return _Graph(edge_index, num_nodes, normalize, lo, hi)
 
-    def fwd_project(self, g, x, wd, out_local):
+    def fwd_project(self, g, x, wd, out_local, push=None):
         out_local.copy_(g.dis[:, None] * (x @ wd.t()))
 
-    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local, hub=None):
+    def fwd_hop1(self, g, p_full, bd, act, z_local, h1_local, hub=None, push=None):
         h = g.dis[:, None] * g.agg(p_full) + bd
         if h1_local is not None:
             h1_local[:h.shape[0]].copy_(h)
@@ -51,7 +51,7 @@ class CpuPhases:
     def bwd_scratch(self, d, r, device):
         return {}
 
-    def bwd_up(self, g, gy, h2_local, wu, scalar, gh2_local, scratch):
+    def bwd_up(self, g, gy, h2_local, wu, scalar, gh2_local, scratch, push=None):
         s = scalar if scalar is not None else torch.ones(1)
         n = gy.shape[0]
         gh2_local.copy_(g.dis[:, None] * s * (gy @ wu))
@@ -66,7 +66,7 @@ class CpuPhases:
         scratch["gu"] = gy.t() @ h2_local[:gy.shape[0]]
         scratch["col"] = gy.sum(0)
 
-    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch, hub=None):
+    def bwd_hop2(self, g, gh2_full, z_local, h1_local, act, gh1_local, scratch, hub=None, push=None):
         gz = g.dis[:, None] * g.agg(gh2_full, transpose=True)
         n = gz.shape[0]
         if act == 1:
