@@ -56,6 +56,11 @@ def workload(args):
     return name, ei, n, s.hidden, s.rank
 
 
+def workload_string(name, n, e, d, r, power_law=False):
+    """config.workload, byte-identical in both arms (ours / --impl reference) so that the driver sees one configuration."""
+    return f"{name}-shaped: N={n} E={e} hidden={d} rank={r}" + (" power-law" if power_law else "")
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -167,6 +172,65 @@ def cpu_model():
     return "unknown"
 
 
+def products_subrecord(lib, dev, steps=8):
+    """BASELINE.json configs[4] (products-shaped, hidden 256, rank 32) on this GPU count, measured in the same run as the
+    headline so that the 1/2/4/8 curve of the second partitioned config is driver-observed (the N > 1 legs carry the same key)."""
+    from gconv_adapter_b200 import GConvAdapter, GraphCache
+    from gconv_adapter_b200.graphs.synthetic import SHAPES, input_rows, make_graph, make_inputs
+    ei, n = make_graph("products", seed=0)
+    s = SHAPES["products"]
+    d, r, e = s.hidden, s.rank, ei.size(1)
+    _, _, params = make_inputs(8, d, r, seed=0)
+    m = GConvAdapter(d, r, learnable_scalar=True)
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k, v in params.items():
+            sd[k].copy_(v)
+    m = m.to(dev)
+    m.graph_cache = GraphCache()
+    eid = ei.to(dev)
+    del ei
+    xd, gd = input_rows(0, n, d, 1234, dev)
+    xd.requires_grad_(True)
+    e_prime = m.graph_for(eid, n).nnz
+
+    def step():
+        xd.grad = None
+        for p in m.parameters():
+            p.grad = None
+        m(xd, eid).backward(gd)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    lib.gca_profile_enable(1)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.gca_profile_report(buf, len(buf))
+    lib.gca_profile_enable(0)
+    prof = json.loads(buf.value.decode())
+    per, a_min = algorithmic_bytes(n, e_prime, d, r)
+    a_gather = a_min - 16 * n * r + 16 * r * e_prime
+    peak, _ = peaks()
+    rec = {"workload": workload_string("products", n, e, d, r), "ms_per_step": ms, "value": e / (ms / 1e3), "unit": UNIT, "n_gpus": 1,
+           "step_alg_bytes": a_min, "frac_of_measured_peak": round(a_min / 1e6 / ms / peak, 4),
+           "gather_bound_bytes": a_gather, "frac_of_measured_peak_on_gather_bound": round(a_gather / 1e6 / ms / peak, 4),
+           "phases_ms": {k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in prof.items()},
+           "variants": {k: v["variant"] for k, v in prof.items() if v["variant"]}}
+    del m, eid, xd, gd
+    torch.cuda.empty_cache()
+    return rec
+
+
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -184,7 +248,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}-shaped: N={n} E={e} hidden={d} rank={r}", "inputs": "host memory (CPU run)"},
+        "config": {"workload": workload_string(name, n, e, d, r, args.power_law), "inputs": "host memory (CPU run)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"full {name}-shaped fwd+bwd x {len(times)} steps; restated PyG GCNConv op sequence "
                                    f"(torch-geometric is not installable here), {cpu_model()}"},
@@ -298,10 +362,12 @@ def run_ours(args):
         # Like a training loop's input prefetch, the copy of step k+1 runs on a copy stream into the second of two device
         # buffers while step k computes; the compute stream waits for the event of the buffer it is about to read.
         x_host = x.pin_memory()
+        y_host = torch.empty_like(x_host).pin_memory()           # the step's result travels back too (4 N d bytes)
         x_bufs = [torch.empty_like(xd), torch.empty_like(xd)]
-        copy_stream = torch.cuda.Stream()
+        copy_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
         copy_done = [torch.cuda.Event(), torch.cuda.Event()]
         buf_free = [torch.cuda.Event(), torch.cuda.Event()]
+        y_ready, y_copied = torch.cuda.Event(), torch.cuda.Event()
         main_stream = torch.cuda.current_stream()
 
         def issue_copy(i):
@@ -319,10 +385,18 @@ def run_ours(args):
             main_stream.wait_event(copy_done[b])
             xin = x_bufs[b].detach().requires_grad_(True)
             y = m(xin, eid)
+            y_ready.record(main_stream)
+            with torch.cuda.stream(d2h_stream):                  # Y -> pinned host memory under the backward of the same step
+                d2h_stream.wait_event(y_ready)
+                y_host.copy_(y.detach(), non_blocking=True)
+                y.record_stream(d2h_stream)
+                y_copied.record(d2h_stream)
             loss = (y * gd).sum()
             loss.backward()
             buf_free[b].record(main_stream)
-            return loss.item()
+            val = loss.item()
+            y_copied.synchronize()                               # the step is over when its result is on the host
+            return val
 
         for b in range(2):
             buf_free[b].record(main_stream)
@@ -340,8 +414,9 @@ def run_ours(args):
         wall = (time.perf_counter() - c0) / k2
         dev_s = t0.elapsed_time(t1) / 1e3 / k2
         e2e = {"value": e / max(wall, dev_s), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-               "d2h_bytes_per_step": 4, "ms_per_step": round(1e3 * max(wall, dev_s), 4), "steps": k2,
-               "h2d": "one X per step from pinned memory, double-buffered: the copy of step k+1 overlaps step k"}
+               "d2h_bytes_per_step": y_host.numel() * 4 + 4, "ms_per_step": round(1e3 * max(wall, dev_s), 4), "steps": k2,
+               "h2d": "one X per step from pinned memory, double-buffered: the copy of step k+1 overlaps step k",
+               "d2h": "Y (4 N d bytes, pinned) on its own stream under the backward of the same step + the scalar loss"}
 
     # ---- CPU baseline (bounded: the oracle at full size takes seconds per step) ----
     cpu = None
@@ -356,8 +431,8 @@ def run_ours(args):
         "metric": METRIC, "value": e / (ms_step / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}-shaped: N={n} E={e} (E'={e_prime} with self loops) hidden={d} rank={r}"
-                               + (" power-law" if args.power_law else ""),
+        "config": {"workload": workload_string(name, n, e, d, r, args.power_law),
+                   "edges_with_self_loops": e_prime,
                    "adapter": "relu, skip, learnable scalar, normalize=True", "graph": "static, structure cached",
                    "l2": "inputs larger than L2 (X, gY, Y, gX are %d MB each)" % (4 * n * d // 1_000_000)
                          if 4 * n * d > 126e6 else "working set fits L2; no flush (latency-bound config)",
@@ -365,6 +440,10 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "step_roofline": step_roofline, "phases": phases, "cpu_baseline": cpu,
     }
+    if args.workload is None and os.environ.get("GCA_BENCH_NO_PRODUCTS", "0") != "1":
+        del xd, gd, eid
+        torch.cuda.empty_cache()
+        line["products"] = products_subrecord(lib, dev)
     print(json.dumps(line))
 
 

@@ -120,3 +120,18 @@ def make_inputs(num_nodes: int, hidden: int, rank: int, seed: int = 0, weight_st
         "conv_up.lin.weight": torch.randn(hidden, rank, generator=g) * weight_std,
     }
     return x, g_out, params
+
+
+def input_rows(lo: int, hi: int, hidden: int, seed: int, device, chunk: int = 65536):
+    """Rows [lo, hi) of the seeded (X, gY) pair of a workload, generated on ``device`` chunk by chunk: chunk c always comes
+    from its own generator seed, so every rank of a partitioned run - and rank 0's full-size reference - draws identical
+    rows without anybody materialising more than it owns."""
+    xs, gs = [], []
+    for c in range(lo // chunk, (max(hi, lo + 1) - 1) // chunk + 1):
+        g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + c)
+        x = torch.randn(chunk, hidden, generator=g, device=device)
+        gy = torch.randn(chunk, hidden, generator=g, device=device)
+        a, b = max(lo, c * chunk) - c * chunk, min(hi, (c + 1) * chunk) - c * chunk
+        xs.append(x[a:b])
+        gs.append(gy[a:b])
+    return torch.cat(xs).contiguous(), torch.cat(gs).contiguous()
