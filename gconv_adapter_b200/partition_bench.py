@@ -50,7 +50,7 @@ def _measure(name, args, lib, dev, rank, world, steps, warmup, with_e2e):
             p.grad = None
         y = m(xd, eid, n)
         y.backward(gd)
-        holder["y"] = y
+        holder["y"] = y.detach()     # (a live y would keep the autograd graph - and its AccumulateGrad nodes - across steps)
 
     for _ in range(max(warmup, 3)):
         step()
@@ -62,7 +62,7 @@ def _measure(name, args, lib, dev, rank, world, steps, warmup, with_e2e):
     pad = lambda t: torch.cat([t, t.new_zeros(s_rows - t.shape[0], t.shape[1])]) if t.shape[0] < s_rows else t
     y_all = [torch.empty(s_rows, d, device=dev) for _ in range(world)] if rank == 0 else None
     gx_all = [torch.empty(s_rows, d, device=dev) for _ in range(world)] if rank == 0 else None
-    dist.gather(pad(holder["y"].detach()), y_all, dst=0)
+    dist.gather(pad(holder["y"]), y_all, dst=0)
     dist.gather(pad(xd.grad), gx_all, dst=0)
     parity = None
     if rank == 0:
