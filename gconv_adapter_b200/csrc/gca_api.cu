@@ -45,6 +45,7 @@ extern "C" int gca_fwd_project(const gca_graph* g, const float* X, int64_t ldx, 
     if (!g || !X || !Wd || !Pp_local || ldx < d) return GCA_ERR_INVALID_ARG;
     if (!shape_ok(d, r) || (ldx % 4) != 0) return GCA_ERR_UNSUPPORTED;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     if (n == 0) return GCA_OK;
     return project_any(r, true, X, ldx, Wd, g->dis, nullptr, Pp_local, n, d, push, static_cast<cudaStream_t>(stream));
 }
@@ -56,6 +57,7 @@ extern "C" int gca_fwd_hop1(const gca_graph* g, const float* Pp_full, const floa
     if (act == GCA_ACT_SILU && !H1_local) return GCA_ERR_INVALID_ARG;
     if (!hub_scratch_ok(g, hub_scratch)) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     return launch_hop(r, false, csr_of(g, false, hub_scratch), Pp_full, bd, act, nullptr, nullptr, Zp_local, H1_local, nullptr,
                       nullptr, n, static_cast<cudaStream_t>(stream), 0, nullptr, push);
 }
@@ -68,6 +70,7 @@ extern "C" int gca_fwd_hop2_up(const gca_graph* g, const float* Zp_full, const f
     if (!shape_ok(d, r) || (ldy % 4) != 0 || (skip && (ldx % 4) != 0)) return GCA_ERR_UNSUPPORTED;
     if (!hub_scratch_ok(g, hub_scratch)) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     return launch_hop_expand(r, true, csr_of(g, false, hub_scratch), Zp_full, Wu, bu, X, ldx, scalar, 1, skip ? 1 : 0, H2_local,
                              Y, ldy, n, d, static_cast<cudaStream_t>(stream));
 }
@@ -84,6 +87,7 @@ extern "C" int gca_bwd_up(const gca_graph* g, const float* gY, int64_t ldg, cons
     if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Scratch S = scratch_ptrs(scratch, d, r);
     GCA_CUDA(cudaMemsetAsync(S.header, 0, 256, st));
@@ -106,6 +110,7 @@ extern "C" int gca_bwd_up_project(const gca_graph* g, const float* gY, int64_t l
     if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Scratch S = scratch_ptrs(scratch, d, r);
     GCA_CUDA(cudaMemsetAsync(S.header, 0, 256, st));
@@ -118,6 +123,7 @@ extern "C" int gca_bwd_up_wgrad(const gca_graph* g, const float* gY, int64_t ldg
     if (!g || !gY || !H2_local || !scratch || ldg < d) return GCA_ERR_INVALID_ARG;
     if (!shape_ok(d, r) || (ldg % 4) != 0) return GCA_ERR_UNSUPPORTED;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     if (n == 0) return GCA_OK;
     const Scratch S = scratch_ptrs(scratch, d, r);
     return wgrad_any(r, gY, ldg, H2_local, nullptr, 0, S.gu, S.col, nullptr, S.header, 0, n, d, static_cast<cudaStream_t>(stream));
@@ -131,6 +137,7 @@ extern "C" int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full, const fl
     if ((act == GCA_ACT_RELU && !Zp_local) || (act == GCA_ACT_SILU && !H1_local)) return GCA_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0 || !hub_scratch_ok(g, hub_scratch)) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     const Scratch S = scratch_ptrs(scratch, 4, r);      // header / bd offsets do not depend on d
     return launch_hop(r, true, csr_of(g, true, hub_scratch), gH2p_full, nullptr, act, Zp_local, H1_local, gH1p_local, nullptr,
                       S.bd, S.header, n, static_cast<cudaStream_t>(stream), 0, nullptr, push);
@@ -146,6 +153,7 @@ extern "C" int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full, con
     if (!shape_ok(d, r) || (ldx % 4) != 0 || (skip && (ldg % 4) != 0) || (gX && (ldgx % 4) != 0)) return GCA_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(scratch) % kAlign) != 0 || !hub_scratch_ok(g, hub_scratch)) return GCA_ERR_WORKSPACE;
     const int n = g->row_end - g->row_begin;
+    const PdlHint pdl_hint(n);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Scratch S = scratch_ptrs(scratch, d, r);
     GCA_TRY(launch_hop_expand(r, false, csr_of(g, true, hub_scratch), gH1p_full, Wd, nullptr, gY, ldg, scalar, 0, skip ? 1 : 0,

@@ -80,10 +80,22 @@ inline int record(cudaError_t e) {
 // launch attribute below the next kernel's CTAs may start (and run their prologue: weight staging into shared
 // memory) while the previous kernel drains.  pdl_wait() blocks until the previous kernel has completed and its
 // writes are visible - it MUST precede the first access to anything a neighbouring kernel reads or writes;
-// pdl_trigger() lets the dependent kernel start launching.
+// pdl_trigger() lets the dependent kernel start launching.  Every kernel triggers at the END of its main loop: a dependent
+// that is launched early stays resident (and keeps being polled) for as long as its primary runs - harmless next to a
+// 20 us kernel, but measured at +25 % on the 0.6-1.3 ms kernels of the products-shaped step (9.5 -> 12.1 ms).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
+// Programmatic launches hide ~1 us of launch gap per kernel boundary: worth 4 us on the 0.36 ms arxiv-shaped step, noise on
+// kernels that run for a millisecond - where they measured HARMFUL (products-shaped step 9.4 ms without, 12.0 ms with,
+// wherever the trigger sits).  Each entry point states its problem size; launches above kPdlMaxRows are plain.
+constexpr int64_t kPdlMaxRows = 1 << 20;
+extern thread_local bool tl_pdl_size_ok;
+struct PdlHint {
+    bool prev;
+    explicit PdlHint(int64_t rows) : prev(tl_pdl_size_ok) { tl_pdl_size_ok = rows <= kPdlMaxRows; }
+    ~PdlHint() { tl_pdl_size_ok = prev; }
+};
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -94,7 +106,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && tl_pdl_size_ok) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -46,6 +46,7 @@ static bool env_flag(const char* name) {
 //   GCA_SPLIT_MB=<n>      gathered operand above n MB: K3 = plain hop + expand-only (default 160)
 bool tc_enabled() { static const bool on = !env_flag("GCA_DISABLE_TC"); return on; }
 bool stream_enabled() { static const bool on = !env_flag("GCA_DISABLE_STREAM"); return on; }
+thread_local bool tl_pdl_size_ok = true;
 bool pdl_enabled() { static const bool on = !env_flag("GCA_DISABLE_PDL"); return on; }
 long long split_bytes() {
     static const long long v = [] { const char* e = getenv("GCA_SPLIT_MB"); return (e ? atoll(e) : 160LL) << 20; }();

@@ -132,7 +132,6 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // what precedes these kernels on the stream is either not ours (an optimizer step may just have written W) or
     // produced the H operand: wait before the first read of anything
     pdl_wait();
-    pdl_trigger();
 
     // contiguous tile ranges: CTA b takes q (+1) consecutive tiles, so its partial covers one row range
     const int ntiles = (p.n + kSRows - 1) / kSRows;
@@ -322,6 +321,7 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(red_full(rbuf));                      // release: the epilogue acquires through its wait
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
+        pdl_trigger();
         return;
     }
 
@@ -505,6 +505,7 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         if (!F16) fold();
+        pdl_trigger();
         // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns 32 bx + 8t .. + 7 ----
         if (active) {
             float* pgp = p.partG + (size_t)bid * R * p.d;

@@ -28,7 +28,7 @@ def test_fwd_project_matches_fp64(n, d, r):
     wd = torch.randn(r, d, device="cuda", generator=gen) * 0.1
     out = torch.full((n, r), float("nan"), device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    _cabi.check(lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out.data_ptr(), d, r, stream), "project")
+    _cabi.check(lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out.data_ptr(), None, d, r, stream), "project")
     torch.cuda.synchronize()
     ref = dis.double()[:, None] * (x.double() @ wd.double().t())
     err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
@@ -37,7 +37,7 @@ def test_fwd_project_matches_fp64(n, d, r):
     assert err < 1e-6, f"max err / max|ref| = {err:.3e}"
     # the same call twice gives the same bits
     out2 = torch.empty_like(out)
-    _cabi.check(lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out2.data_ptr(), d, r, stream), "project")
+    _cabi.check(lib.gca_fwd_project(g.handle, x.data_ptr(), x.stride(0), wd.data_ptr(), out2.data_ptr(), None, d, r, stream), "project")
     assert torch.equal(out, out2)
 
 
@@ -82,8 +82,8 @@ def test_backward_dense_phases_match_fp64(n, d, r, with_scalar):
 
     def run():
         _cabi.check(lib.gca_bwd_up(g.handle, gy.data_ptr(), gy.stride(0), h2.data_ptr(), wu.data_ptr(), sp, gh2.data_ptr(),
-                                   scratch.data_ptr(), d, r, st), "bwd_up")
-        _cabi.check(lib.gca_bwd_hop2(g.handle, gh2.data_ptr(), z.data_ptr(), None, 1, gh1.data_ptr(), scratch.data_ptr(), hp, r, st),
+                                   scratch.data_ptr(), None, d, r, st), "bwd_up")
+        _cabi.check(lib.gca_bwd_hop2(g.handle, gh2.data_ptr(), z.data_ptr(), None, 1, gh1.data_ptr(), scratch.data_ptr(), hp, None, r, st),
                     "bwd_hop2")
         _cabi.check(lib.gca_bwd_hop1_down(g.handle, gh1.data_ptr(), x.data_ptr(), x.stride(0), gy.data_ptr(), gy.stride(0),
                                           wd.data_ptr(), sp, 1, gp.data_ptr(), gx.data_ptr(), gx.stride(0), scratch.data_ptr(), hp,
