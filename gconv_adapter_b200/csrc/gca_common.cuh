@@ -80,9 +80,7 @@ inline int record(cudaError_t e) {
 // launch attribute below the next kernel's CTAs may start (and run their prologue: weight staging into shared
 // memory) while the previous kernel drains.  pdl_wait() blocks until the previous kernel has completed and its
 // writes are visible - it MUST precede the first access to anything a neighbouring kernel reads or writes;
-// pdl_trigger() lets the dependent kernel start launching.  Every kernel triggers at the END of its main loop: a dependent
-// that is launched early stays resident (and keeps being polled) for as long as its primary runs - harmless next to a
-// 20 us kernel, but measured at +25 % on the 0.6-1.3 ms kernels of the products-shaped step (9.5 -> 12.1 ms).
+// pdl_trigger() lets the dependent kernel start launching (kernels trigger right after their own prologue).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();

@@ -20,6 +20,7 @@ k_hub_partials(const int* __restrict__ rowptr, const int* __restrict__ colidx, c
                float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     pdl_wait();
+    pdl_trigger();
     const int nitems = *nitems_ptr;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPG, grp = lane / LPG;
@@ -35,7 +36,6 @@ k_hub_partials(const int* __restrict__ rowptr, const int* __restrict__ colidx, c
         for (int off = LPG; off < 32; off <<= 1) part = f4_add(part, f4_shfl_xor(part, off));
         if (grp == 0) *reinterpret_cast<float4*>(hub_part + (size_t)item * R + sub * 4) = part;
     }
-    pdl_trigger();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -54,6 +54,7 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
     const int sub = lane % LPG, grp = lane / LPG;
     const int wglobal = blockIdx.x * (blockDim.x >> 5) + warp, wtotal = gridDim.x * (blockDim.x >> 5);
     pdl_wait();
+    pdl_trigger();
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!BWD && bias) b4 = ldg4(bias + sub * 4);
     float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -90,7 +91,6 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
             for (int hp = 0; hp < push.count; ++hp) *reinterpret_cast<float4*>(push.dst[hp] + o) = go;
         }
     }
-    pdl_trigger();
     if (BWD) {
         __shared__ float s_gb[8][R];
 #pragma unroll

@@ -349,6 +349,7 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
+    pdl_trigger();
 
     const int ntiles = (n + kTcRows - 1) / kTcRows;
     // i-th tile of this CTA (or -1 after the last one); every consumer warp calls this exactly once per i, in order
@@ -592,7 +593,6 @@ k_hop_expand_tc(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
     }
     tc::tc_fence_before();
     __syncthreads();
-    pdl_trigger();          // after the barrier: the idle warps get here at once, the working warps when the last tile is done
     if (warp == 8) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);

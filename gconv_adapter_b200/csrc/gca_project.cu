@@ -137,6 +137,7 @@ __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, in
         Wq[idx] = q;
     }
     __syncthreads();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const float sc_s = scalar ? __ldg(scalar) : 1.f;
@@ -210,7 +211,6 @@ __device__ __forceinline__ void project_mma_body(const float* __restrict__ A, in
             if (r1 < n) *reinterpret_cast<float2*>(out + (size_t)r1 * R + j * 8 + 2 * t) = make_float2(v[2] * sc1, v[3] * sc1);
         }
     }
-    pdl_trigger();
 }
 
 template <int R, bool W_IS_RD>

@@ -51,8 +51,11 @@ constexpr int kSEpi = 2;                   // epilogue warps of the projection r
 
 // MMA warps per box of the projection role (two - one 16-row m-tile each - measured no faster than one: 43.7 vs 44.0 us)
 __host__ __device__ constexpr int proj_split(int r, bool proj, bool wgrad) { return (void)r, (void)proj, (void)wgrad, 1; }
-__host__ __device__ constexpr int stream_threads(int r, bool proj, bool wgrad) {
-    return 32 * (1 + (proj ? kSWarps * proj_split(r, proj, wgrad) + kSEpi : 0) + (wgrad ? kSWarps : 0));
+// PROJ + WGRAD with the fp16 split runs both on ONE set of warps ("fused role", see k_dense_stream)
+__host__ __device__ constexpr bool fused_role(bool proj, bool wgrad, bool f16) { return proj && wgrad && f16; }
+__host__ __device__ constexpr int stream_threads(int r, bool proj, bool wgrad, bool f16) {
+    return fused_role(proj, wgrad, f16) ? 32 * (1 + 2 * kSWarps + kSEpi)
+                                        : 32 * (1 + (proj ? kSWarps * proj_split(r, proj, wgrad) + kSEpi : 0) + (wgrad ? kSWarps : 0));
 }
 
 struct StreamParams {
@@ -97,6 +100,13 @@ __device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv)
     scale = __uint_as_float((uint32_t)(267 - e) << 23);
     inv = __uint_as_float((uint32_t)(e - 13) << 23);
 }
+// 8 x 8 b16 transpose across the warp: a projection A-fragment register (lane (g, t) holds row g, k = 2t, 2t+1) becomes
+// the weight-gradient B-fragment register of the same block (lane (g, t) holds k = rows 2t, 2t+1 ; n = column g)
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
 // (x0, x1) * scale -> packed halves {low = element 0}: hi = rn(.), lo = rn(. - hi)
 __device__ __forceinline__ void split_h2(float x0, float x1, float scale, uint32_t& hi, uint32_t& lo) {
     const float a0 = x0 * scale, a1 = x1 * scale;
@@ -108,13 +118,15 @@ __device__ __forceinline__ void split_h2(float x0, float x1, float scale, uint32
 }
 
 template <int R, bool PROJ, bool WGRAD, bool DOT, bool W_IS_RD, bool F16>
-__global__ void __launch_bounds__(stream_threads(R, PROJ, WGRAD), 1)
+__global__ void __launch_bounds__(stream_threads(R, PROJ, WGRAD, F16), 1)
 k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const StreamParams p) {
     constexpr int NT = R / 8, MT = R / 16;
     constexpr int PW = proj_split(R, PROJ, WGRAD);          // MMA warps per box of the projection role
     constexpr int kProjWarps = kSWarps * PW;
-    constexpr int kConsumers = (PROJ ? kProjWarps : 0) + (WGRAD ? kSWarps : 0);
+    constexpr bool FUSED = fused_role(PROJ, WGRAD, F16);
+    constexpr int kFusedWarps = 2 * kSWarps;              // fused role: (box, m-tile) per warp
+    constexpr int kConsumers = FUSED ? kFusedWarps : (PROJ ? kProjWarps : 0) + (WGRAD ? kSWarps : 0);
     extern __shared__ uint8_t smem_unaligned[];
     uint8_t* smem = smem_unaligned + ((1024u - (smem_addr(smem_unaligned) & 1023u)) & 1023u);
     const uint32_t bar0 = smem_addr(smem + p.bar_off);
@@ -125,13 +137,14 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), kConsumers); }
-        for (int b = 0; b < 2; ++b) { mbar_init(red_full(b), kProjWarps); mbar_init(red_free(b), kSEpi); }
+        for (int b = 0; b < 2; ++b) { mbar_init(red_full(b), FUSED ? kFusedWarps : kProjWarps); mbar_init(red_free(b), kSEpi); }
         mbar_fence_init();
     }
     __syncthreads();
     // what precedes these kernels on the stream is either not ours (an optimizer step may just have written W) or
     // produced the H operand: wait before the first read of anything
     pdl_wait();
+    pdl_trigger();
 
     // contiguous tile ranges: CTA b takes q (+1) consecutive tiles, so its partial covers one row range
     const int ntiles = (p.n + kSRows - 1) / kSRows;
@@ -165,7 +178,201 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cw = warp - 1;
     const int g = lane >> 2, t = lane & 3;
 
-    if (PROJ && cw < kProjWarps) {
+    if (FUSED && cw < kFusedWarps) {
+        // ===================== fused role (PROJ + WGRAD, fp16 split): one conversion serves both products =====================
+        // Warp (w, mt) owns the 16-row m-tile mt of box w of every tile (16 warps: four per scheduler hide each other's
+        // shuffle-max -> convert -> HMMA -> movmatrix -> HMMA chains; with 8 warps the same work ran at 27 % issue utilisation).
+        // It converts its 16 x 32 half box ONCE into projection A-fragments (fp16 hi / lo, its own power-of-two scale),
+        // multiplies them with its W fragments (-> [16, R] partial, as the projection role),
+        // then transposes every fragment register with movmatrix: the 8 x 8 block (row pg(g), columns C(2t), C(2t+1)) turns
+        // into (rows pg(2t), pg(2t+1) ; column C(g)) = the B-fragment of the weight gradient over the SAME 16 rows
+        // (k = rows of m-tile mt, n-tiles 2 kb2 / 2 kb2 + 1 = the even / odd column pairs of the 16-column block kb2).
+        // Through the permutations lane (g, t) ends up owning G[c = g (+8)][32 w + 16 kb2 + 4t .. + 3]: a float4.
+        if constexpr (FUSED) {
+        const int bx = cw % kSWarps, mt = cw / kSWarps;
+        const bool active = bx < p.nb;
+        uint32_t wf[2][NT][4];
+        float inv_w = 1.f;
+        {
+            float wv[2][NT][4];
+            float m = 0.f;
+#pragma unroll
+            for (int kb2 = 0; kb2 < 2; ++kb2)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k_ = 32 * bx + 16 * kb2 + 4 * t + e, c = nt * 8 + g;
+                        wv[kb2][nt][e] = !active ? 0.f : (W_IS_RD ? __ldg(p.W + (size_t)c * p.d + k_) : __ldg(p.W + (size_t)k_ * R + c));
+                        m = fmaxf(m, fabsf(wv[kb2][nt][e]));
+                    }
+            float sw;
+            pow2_scale(warp_max(m), sw, inv_w);
+#pragma unroll
+            for (int kb2 = 0; kb2 < 2; ++kb2)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    split_h2(wv[kb2][nt][0], wv[kb2][nt][1], sw, wf[kb2][nt][0], wf[kb2][nt][2]);
+                    split_h2(wv[kb2][nt][2], wv[kb2][nt][3], sw, wf[kb2][nt][1], wf[kb2][nt][3]);
+                }
+        }
+        const int pg = (g >> 1) + 4 * (g & 1);
+        const float sc_s = p.scalar ? __ldg(p.scalar) : 1.f;
+        float4* red = reinterpret_cast<float4*>(smem + p.red_off);
+        constexpr int kSlots = 2 * NT * 32;
+        float run[MT][2][2][4];                                              // [c m-tile][kb2][even / odd pair][c-fragment]
+        float4 csum[2];                                                      // column sums of this lane's 8 columns (its rows)
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ < 2; ++b_)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) run[m][a_][b_][i] = 0.f;
+        csum[0] = csum[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto hload = [&](const uint8_t* ht, int row, int c) -> float {
+            if (R == 32) return *reinterpret_cast<const float*>(ht + box_off(row, c >> 2) + (c & 3) * 4);
+            return *reinterpret_cast<const float*>(ht + (row * R + c) * 4);
+        };
+        int s = 0;
+        uint32_t ph = 0;
+        for (int k = 0; k < my_tiles; ++k) {
+            float accp[2][NT][4];                                            // projection: [hi.hi / corrections][nt]
+#pragma unroll
+            for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) accp[a_][nt][i] = 0.f;
+            float sc[2], inv_x = 1.f;
+            mbar_wait(full(s), ph);
+            const uint8_t* stg = smem + (size_t)s * p.stage_bytes;
+            const uint8_t* box = stg + bx * kSBox;
+            const uint8_t* ht = stg + p.h_off;
+            const float* scs = reinterpret_cast<const float*>(stg + p.sc_off);
+            sc[0] = (p.rowscale ? scs[16 * mt + pg] : 1.f) * sc_s * inv_w;
+            sc[1] = (p.rowscale ? scs[16 * mt + pg + 8] : 1.f) * sc_s * inv_w;
+            if (active) {
+                {
+                    // ---- this m-tile's 16 rows x 32 columns and its H rows: load, scale, split ----
+                    float4 x[2][2];                                          // [kb2][row pg / pg + 8]
+                    float m = 0.f;
+#pragma unroll
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+                        x[kb2][0] = lds4(box + box_off(16 * mt + pg, 4 * kb2 + t));
+                        x[kb2][1] = lds4(box + box_off(16 * mt + pg + 8, 4 * kb2 + t));
+                        m = absmax4(absmax4(m, x[kb2][0]), x[kb2][1]);
+                        csum[kb2] = f4_add(csum[kb2], f4_add(x[kb2][0], x[kb2][1]));
+                    }
+                    float hv[MT][8];
+                    float mh = 0.f;
+#pragma unroll
+                    for (int cm = 0; cm < MT; ++cm)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            // q: bit 0 = row t / t + 4 (k = 2t / 2t+1), bit 1 = c + 8, bit 2 = rows + 8 (k + 8)
+                            hv[cm][q] = hload(ht, 16 * mt + 8 * (q >> 2) + t + 4 * (q & 1), 16 * cm + g + 8 * ((q >> 1) & 1));
+                            mh = fmaxf(mh, fabsf(hv[cm][q]));
+                        }
+                    float sx, sh, inv_h;
+                    pow2_scale(warp_max(m), sx, inv_x);
+                    pow2_scale(warp_max(mh), sh, inv_h);
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+                        split_h2(x[kb2][0].x, x[kb2][0].y, sx, ah[kb2][0], al[kb2][0]);
+                        split_h2(x[kb2][1].x, x[kb2][1].y, sx, ah[kb2][1], al[kb2][1]);
+                        split_h2(x[kb2][0].z, x[kb2][0].w, sx, ah[kb2][2], al[kb2][2]);
+                        split_h2(x[kb2][1].z, x[kb2][1].w, sx, ah[kb2][3], al[kb2][3]);
+                    }
+                    // ---- projection: [16 rows, R] += box[16, 32] W[32, R] ----
+#pragma unroll
+                    for (int kb2 = 0; kb2 < 2; ++kb2)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            mma_f16(accp[0][nt], ah[kb2], wf[kb2][nt][0], wf[kb2][nt][1]);
+                            mma_f16(accp[1][nt], al[kb2], wf[kb2][nt][0], wf[kb2][nt][1]);
+                            mma_f16(accp[1][nt], ah[kb2], wf[kb2][nt][2], wf[kb2][nt][3]);
+                        }
+                    // ---- weight gradient over the same 16 rows: B = transposed fragments, A = H^T ----
+                    uint32_t hh[MT][4], hl[MT][4];
+#pragma unroll
+                    for (int cm = 0; cm < MT; ++cm) {
+                        split_h2(hv[cm][0], hv[cm][1], sh, hh[cm][0], hl[cm][0]);     // c = g,   k = 2t, 2t+1
+                        split_h2(hv[cm][2], hv[cm][3], sh, hh[cm][1], hl[cm][1]);     // c = g+8
+                        split_h2(hv[cm][4], hv[cm][5], sh, hh[cm][2], hl[cm][2]);     // c = g,   k = 2t+8, 2t+9
+                        split_h2(hv[cm][6], hv[cm][7], sh, hh[cm][3], hl[cm][3]);     // c = g+8
+                    }
+                    const float f = inv_x * inv_h;
+#pragma unroll
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+                        uint32_t bh[4], bl[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { bh[i] = movmatrix_trans(ah[kb2][i]); bl[i] = movmatrix_trans(al[kb2][i]); }
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr) {                     // n-tile = even / odd column pairs: registers {0,1} / {2,3}
+#pragma unroll
+                            for (int cm = 0; cm < MT; ++cm) {
+                                float accw[4] = {0.f, 0.f, 0.f, 0.f};
+                                mma_f16(accw, hh[cm], bh[2 * pr], bh[2 * pr + 1]);
+                                mma_f16(accw, hl[cm], bh[2 * pr], bh[2 * pr + 1]);
+                                mma_f16(accw, hh[cm], bl[2 * pr], bl[2 * pr + 1]);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) run[cm][kb2][pr][i] = fmaf(accw[i], f, run[cm][kb2][pr][i]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(s));
+            const int rbuf = k & 1;
+            if (k >= 2) mbar_wait(red_free(rbuf), (uint32_t)(((k >> 1) - 1) & 1));
+            float4* mine = red + ((size_t)rbuf * kSWarps + bx) * kSlots;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                mine[(mt * NT + nt) * 32 + lane] =
+                    make_float4((accp[0][nt][0] + accp[1][nt][0]) * inv_x * sc[0], (accp[0][nt][1] + accp[1][nt][1]) * inv_x * sc[0],
+                                (accp[0][nt][2] + accp[1][nt][2]) * inv_x * sc[1], (accp[0][nt][3] + accp[1][nt][3]) * inv_x * sc[1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(red_full(rbuf));
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        // ---- per-CTA partial.  c-fragment of n-tile (kb2, pr): c0 = (c = g, n = 2t) -> column 16 kb2 + 4t + 2 pr, c1 = (g, 2t+1) ->
+        //      + 1, c2 / c3 = c + 8: lane (g, t) owns G[c][32 bx + 16 kb2 + 4t .. + 3] for c = g, g + 8 (+ 16 cm) ----
+        //      Every CTA emits TWO partials (one per m-tile half): 2 * grid <= kMaxParts rows for k_finalize.
+        const int pid = 2 * bid + mt;
+        if (active) {
+            float* pgp = p.partG + (size_t)pid * R * p.d;
+#pragma unroll
+            for (int cm = 0; cm < MT; ++cm)
+#pragma unroll
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
+                    const int col = 32 * bx + 16 * kb2 + 4 * t;
+                    *reinterpret_cast<float4*>(pgp + (size_t)(16 * cm + g) * p.d + col) =
+                        make_float4(run[cm][kb2][0][0], run[cm][kb2][0][1], run[cm][kb2][1][0], run[cm][kb2][1][1]);
+                    *reinterpret_cast<float4*>(pgp + (size_t)(16 * cm + g + 8) * p.d + col) =
+                        make_float4(run[cm][kb2][0][2], run[cm][kb2][0][3], run[cm][kb2][1][2], run[cm][kb2][1][3]);
+                }
+            if (p.partCol) {
+                // this lane summed rows pg(g), pg(g) + 8 (+ 16) of its 8 columns: add the 8 row groups (lanes with equal t)
+#pragma unroll
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
+                    float4 c4 = csum[kb2];
+                    c4 = f4_add(c4, f4_shfl_xor(c4, 4));
+                    c4 = f4_add(c4, f4_shfl_xor(c4, 8));
+                    c4 = f4_add(c4, f4_shfl_xor(c4, 16));
+                    if (g == 0) *reinterpret_cast<float4*>(p.partCol + (size_t)pid * p.d + 32 * bx + 16 * kb2 + 4 * t) = c4;
+                }
+            }
+        }
+        if (bid == 0 && cw == 0 && lane == 0) p.header[p.slot] = 2 * (int)gridDim.x;
+        }
+        return;
+    }
+
+    if (!FUSED && PROJ && cw < kProjWarps) {
         // ===================== projection warps =====================
         const int bx = cw % kSWarps;
         const int mt_lo = PW == 2 ? cw / kSWarps : 0, mt_hi = PW == 2 ? mt_lo + 1 : 2;   // m-tiles of this warp
@@ -321,16 +528,15 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(red_full(rbuf));                      // release: the epilogue acquires through its wait
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        pdl_trigger();
         return;
     }
 
-    if (PROJ && cw < kProjWarps + kSEpi) {
+    if (PROJ && cw < (FUSED ? kFusedWarps : kProjWarps) + kSEpi) {
         // ===================== projection epilogue warps =====================
         constexpr int kSlots = 2 * NT * 32;
         constexpr int kPer = kSlots / (kSEpi * 32);                          // fragment slots per thread (2 at r = 16)
         const float4* red = reinterpret_cast<const float4*>(smem + p.red_off);
-        const int th = (cw - kProjWarps) * 32 + lane;
+        const int th = (cw - (FUSED ? kFusedWarps : kProjWarps)) * 32 + lane;
         for (int k = 0; k < my_tiles; ++k) {
             const int rbuf = k & 1;
             mbar_wait(red_full(rbuf), (uint32_t)((k >> 1) & 1));
@@ -360,7 +566,7 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return;
     }
 
-    if (WGRAD) {
+    if (WGRAD && !FUSED) {
         // ===================== weight-gradient warps =====================
         const int bx = PROJ ? cw - kProjWarps - kSEpi : cw;
         const bool active = bx < p.nb;
@@ -505,7 +711,6 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         if (!F16) fold();
-        pdl_trigger();
         // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns 32 bx + 8t .. + 7 ----
         if (active) {
             float* pgp = p.partG + (size_t)bid * R * p.d;
@@ -549,16 +754,16 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
                int grid, const char* name, cudaStream_t st) {
     // GCA_STREAM_TF32=1 selects the 3xTF32 products instead of the scaled 2xFP16 split (A/B runs, tests)
     static const bool tf32 = [] { const char* e = getenv("GCA_STREAM_TF32"); return e && e[0] == '1'; }();
-    const int threads = stream_threads(R, PROJ, WGRAD);
+
     ProfScope ps(name, st, tf32 ? "stream_tf32" : "stream_f16");
     if (tf32) {
         auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD, false>;
         GCA_TRY(set_smem(kern, smem));
-        GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmH, p));
+        GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(stream_threads(R, PROJ, WGRAD, false)), smem, st, tmA, tmB, tmH, p));
     } else {
         auto kern = k_dense_stream<R, PROJ, WGRAD, DOT, W_IS_RD, true>;
         GCA_TRY(set_smem(kern, smem));
-        GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmH, p));
+        GCA_CUDA(launch_pdl(kern, dim3(grid), dim3(stream_threads(R, PROJ, WGRAD, true)), smem, st, tmA, tmB, tmH, p));
     }
     GCA_LAUNCH_OK();
     return GCA_OK;

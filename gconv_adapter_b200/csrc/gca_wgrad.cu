@@ -158,6 +158,7 @@ __device__ __forceinline__ void wgrad_stream_body(const float* __restrict__ A, i
     float4* run = reinterpret_cast<float4*>(smem + 4 * QPB);   // [4 * MT][256]
     __shared__ float s_dot[8];
     pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int cb = col_base + warp * 32;
@@ -268,7 +269,6 @@ __device__ __forceinline__ void wgrad_stream_body(const float* __restrict__ A, i
             }
         if (c + 1 < nch) hstore((c + 1) & 1);
     }
-    pdl_trigger();
     // ---- per-CTA partial: lane (g, t) owns rows c = g, g+8 (+16 m) and columns cb+8t .. cb+8t+7 ----
     float* pg = partG + (size_t)bid * R * d;
     const int oc = cb + 8 * t;
