@@ -537,10 +537,16 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kPer = kSlots / (kSEpi * 32);                          // fragment slots per thread (2 at r = 16)
         const float4* red = reinterpret_cast<const float4*>(smem + p.red_off);
         const int th = (cw - (FUSED ? kFusedWarps : kProjWarps)) * 32 + lane;
+        // The summed tile is staged as [32][R] floats (two buffers) so that it leaves as whole rows: the tile is ONE
+        // contiguous block of 32 R floats in `out` and in every peer's gathered buffer, written with 512 contiguous bytes
+        // per warp instruction (8-byte fragment stores ran the NVLink pushes at a third of that).
+        float* outs = reinterpret_cast<float*>(smem + p.bar_off + 256);     // [2][kSRows][R]
+        constexpr int kF4 = kSRows * R / 4;                                  // float4 per tile
         for (int k = 0; k < my_tiles; ++k) {
             const int rbuf = k & 1;
             mbar_wait(red_full(rbuf), (uint32_t)((k >> 1) & 1));
             const float4* rb = red + (size_t)rbuf * kSWarps * kSlots;
+            float* ot = outs + (size_t)rbuf * kSRows * R;
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
                 const int idx = th + u * kSEpi * 32;
@@ -549,19 +555,23 @@ k_dense_stream(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int w = 1; w < kSWarps; ++w) v = f4_add(v, rb[w * kSlots + idx]);   // box order: fixed
                 const int slot = idx >> 5, g2 = (idx & 31) >> 2, t2 = idx & 3;
                 const int mt = slot / NT, nt = slot - mt * NT;
-                const int row_a = (t0 + k) * kSRows + 16 * mt + (g2 >> 1) + 4 * (g2 & 1);
-                const size_t oa = (size_t)row_a * R + nt * 8 + 2 * t2, ob = oa + 8 * R;
-                if (row_a < p.n) {
-                    *reinterpret_cast<float2*>(p.out + oa) = make_float2(v.x, v.y);
-                    for (int hp = 0; hp < p.push.count; ++hp) *reinterpret_cast<float2*>(p.push.dst[hp] + oa) = make_float2(v.x, v.y);
-                }
-                if (row_a + 8 < p.n) {
-                    *reinterpret_cast<float2*>(p.out + ob) = make_float2(v.z, v.w);
-                    for (int hp = 0; hp < p.push.count; ++hp) *reinterpret_cast<float2*>(p.push.dst[hp] + ob) = make_float2(v.z, v.w);
-                }
+                const int lr = 16 * mt + (g2 >> 1) + 4 * (g2 & 1);
+                *reinterpret_cast<float2*>(ot + lr * R + nt * 8 + 2 * t2) = make_float2(v.x, v.y);
+                *reinterpret_cast<float2*>(ot + (lr + 8) * R + nt * 8 + 2 * t2) = make_float2(v.z, v.w);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(red_free(rbuf));
+            if (lane == 0) mbar_arrive(red_free(rbuf));                      // the partial buffers are free again
+            named_sync(3, kSEpi * 32);                                       // tile staged by both epilogue warps
+            const size_t base4 = (size_t)(t0 + k) * kF4;
+            const int rows_left = p.n - (t0 + k) * kSRows;
+            const int lim4 = (rows_left >= kSRows ? kSRows : (rows_left > 0 ? rows_left : 0)) * (R / 4);
+            for (int q = th; q < lim4; q += kSEpi * 32) {
+                const float4 v = reinterpret_cast<const float4*>(ot)[q];
+                reinterpret_cast<float4*>(p.out)[base4 + q] = v;
+                for (int hp = 0; hp < p.push.count; ++hp) reinterpret_cast<float4*>(p.push.dst[hp])[base4 + q] = v;
+            }
+            // (two staging buffers: tile k+1 is staged into the other one; the barrier of tile k+1 orders these reads
+            //  before anybody stages tile k+2 into this one)
         }
         return;
     }
@@ -802,14 +812,15 @@ int launch_dense_stream_t(const DenseStreamArgs& a, cudaStream_t st) {
         p.stage_bytes = (p.sc_off + sc_bytes + 1023u) & ~1023u;
         p.tx_bytes = p.sc_off + sc_bytes;
         const size_t red_bytes = proj ? (size_t)2 * kSWarps * (2 * NT * 32) * 16 : 0;
-        const size_t fixed = red_bytes + 256 + 1024;                 // partials + barriers / dot scratch + alignment slack
+        const size_t out_bytes = proj ? (size_t)2 * kSRows * R * 4 : 0;       // staged output tiles of the projection epilogue
+        const size_t fixed = red_bytes + 256 + out_bytes + 1024;     // partials + barriers / dot scratch + staging + alignment slack
         int stages = (int)((227 * 1024 - fixed) / p.stage_bytes);
         if (stages > 8) stages = 8;
         if (stages < 2) return GCA_ERR_UNSUPPORTED;
         p.stages = stages;
         p.red_off = (uint32_t)stages * p.stage_bytes;
         p.bar_off = p.red_off + (uint32_t)red_bytes;
-        const size_t smem = (size_t)p.bar_off + 256 + 1024;
+        const size_t smem = (size_t)p.bar_off + 256 + out_bytes + 1024;
         CUtensorMap tmA, tmB, tmH;
         if (!get_box_map(&tmA, a.A, a.n, a.d, a.lda, 32, kSRows, true)) return GCA_ERR_UNSUPPORTED;
         tmB = tmA; tmH = tmA;

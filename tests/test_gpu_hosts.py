@@ -8,7 +8,7 @@ import torch
 
 from gconv_adapter_b200 import GConvAdapter
 from gconv_adapter_b200.graphs.synthetic import make_graph, molecule_batch
-from gconv_adapter_b200.layers.hosts import MolecularGraphPredictionHost, TransductiveHost
+from hosts import MolecularGraphPredictionHost, TransductiveHost
 from oracle.pyg_restated import GConvAdapterRef
 
 from util import assert_close

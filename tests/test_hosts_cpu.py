@@ -5,7 +5,7 @@ import functools
 import torch
 
 from gconv_adapter_b200.graphs.synthetic import molecule_batch, symmetric_random_graph
-from gconv_adapter_b200.layers.hosts import MolecularGraphPredictionHost, TransductiveHost
+from hosts import MolecularGraphPredictionHost, TransductiveHost
 from oracle.pyg_restated import GConvAdapterRef
 
 
