@@ -280,6 +280,9 @@ def run_host_workload(args, lib, dev):
         d, r, layers, calls = 300, 16, 5, 5
         host = MolecularGraphPredictionHost(layers, d, 1)
         host.add_adapter(functools.partial(GConvAdapter, bottleneck_size=r, learnable_scalar=True), ["post"], "sequential")
+        for a in host.modules():
+            if isinstance(a, GConvAdapter):
+                a.validate_edge_index = "lazy"      # a new graph every step: no stream synchronisation per build
         pool = []
         for i in range(16):                       # 16 distinct batches > graph-cache capacity (8): every step is a cache miss
             ei, batch, n = molecule_batch(batch_size=32, seed=100 + i)
@@ -291,7 +294,7 @@ def run_host_workload(args, lib, dev):
         n_step = sum(b[0].size(0) for b in pool) / len(pool)
         dev_pool = [tuple(t.to(dev) for t in b) for b in pool]
         host_pool = [tuple(t.pin_memory() for t in b) for b in pool]
-        graph_note = "new edge_index every step: structure rebuilt in the timed region (16 batches cycle through a cache of 8)"
+        graph_note = "new edge_index every step: structure rebuilt in the timed region (16 batches cycle through a cache of 8), node ids validated lazily (no sync)"
 
         def run(batch):
             x, ei, ea, bt = batch

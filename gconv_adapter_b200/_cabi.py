@@ -56,11 +56,13 @@ SIGNATURES = {
     "gca_graph_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "gca_graph_build": (C.c_int, [_f, _f, _i64, _i32, _i32, _i32, C.c_int, _f, _sz, _f, C.POINTER(C.c_void_p)]),
     "gca_graph_validate": (C.c_int, [_f, _f, C.POINTER(_i64), C.POINTER(_i64)]),
+    "gca_graph_validate_async": (C.c_int, [_f, _f, _f]),
+    "gca_graph_validate_finish": (C.c_int, [_f, _f, C.POINTER(_i64), C.POINTER(_i64)]),
     "gca_graph_destroy": (None, [_f]),
     "gca_graph_get_view": (C.c_int, [_f, C.POINTER(GraphView)]),
     "gca_graph_edge_coef": (C.c_int, [_f, _f, _f]),
     "gca_hub_scratch_bytes": (_sz, [_f]),
-    "gca_propagate": (C.c_int, [_f, C.c_int, _f, _i64, _f, _i64, _i32, _f]),
+    "gca_propagate": (C.c_int, [_f, C.c_int, _f, _i64, _f, _i64, _f, _f, _i32, _f]),
     "gca_fwd_project": (C.c_int, [_f, _f, _i64, _f, _f, C.POINTER(Push), _i32, _i32, _f]),
     "gca_fwd_hop1": (C.c_int, [_f, _f, _f, C.c_int, _f, _f, _f, C.POINTER(Push), _i32, _f]),
     "gca_fwd_hop2_up": (C.c_int, [_f, _f, _f, _i64, _f, _f, _f, C.c_int, _f, _f, _i64, _f, _i32, _i32, _f]),

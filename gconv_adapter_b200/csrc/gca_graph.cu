@@ -422,6 +422,23 @@ extern "C" int gca_graph_validate(gca_graph* g, gca_stream_t stream_, int64_t* n
     return h[0] ? GCA_ERR_INDEX_RANGE : GCA_OK;
 }
 
+// Deferred validation: gca_graph_validate synchronises the stream on every build - once per step when the graph changes
+// every step (batched molecules).  The asynchronous pair copies the flags into caller-owned PINNED host memory (5 x int32)
+// on the stream; the caller polls an event it recorded after this call and then lets _finish read them (host only).
+extern "C" int gca_graph_validate_async(const gca_graph* g, int32_t* host_flags5, gca_stream_t stream_) {
+    if (!g || !host_flags5) return GCA_ERR_INVALID_ARG;
+    GCA_CUDA(cudaMemcpyAsync(host_flags5, g->flags, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream_)));
+    return GCA_OK;
+}
+extern "C" int gca_graph_validate_finish(gca_graph* g, const int32_t* host_flags5, int64_t* nnz, int64_t* nnz_t) {
+    if (!g || !host_flags5) return GCA_ERR_INVALID_ARG;
+    if (nnz) *nnz = host_flags5[1];
+    if (nnz_t) *nnz_t = host_flags5[2];
+    g->nitems = host_flags5[3];
+    g->nitems_t = host_flags5[4];
+    return host_flags5[0] ? GCA_ERR_INDEX_RANGE : GCA_OK;
+}
+
 extern "C" void gca_graph_destroy(gca_graph* g) { delete g; }
 
 extern "C" int gca_graph_get_view(const gca_graph* g, gca_graph_view* v) {

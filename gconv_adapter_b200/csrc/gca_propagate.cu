@@ -16,8 +16,9 @@ using namespace gca;
 // CSR by source: the adjoint, used for the backward.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_propagate(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
-            const float* __restrict__ X, int64_t ldx, float* __restrict__ out, int64_t ldo, int n, int D, int row_begin) {
+k_propagate(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ nbr_scale,
+            const float* __restrict__ row_scale, const float* __restrict__ X, int64_t ldx, float* __restrict__ out, int64_t ldo,
+            int n, int D) {
     const int lane = threadIdx.x & 31;
     const int nblk = (D + 127) / 128;
     const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -31,7 +32,7 @@ k_propagate(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
         for (int e = beg; e < end; e += 8) {
             int jm = -1;
             float dm = 0.f;
-            if (lane < 8 && e + lane < end) { jm = __ldg(colidx + e + lane); dm = __ldg(dis + jm); }
+            if (lane < 8 && e + lane < end) { jm = __ldg(colidx + e + lane); dm = __ldg(nbr_scale + jm); }
             float4 v[8];
             float w[8];
 #pragma unroll
@@ -47,14 +48,14 @@ k_propagate(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
             }
         }
         if (col_ok) {
-            const float di = __ldg(dis + row_begin + row);
+            const float di = __ldg(row_scale + row);
             *reinterpret_cast<float4*>(out + (size_t)row * ldo + col) = f4_scale(acc, di);
         }
     }
 }
 
 extern "C" int gca_propagate(const gca_graph* g, int transpose, const float* X_full, int64_t ldx, float* out_local, int64_t ldo,
-                             int32_t D, gca_stream_t stream) {
+                             const float* src_scale, const float* dst_scale, int32_t D, gca_stream_t stream) {
     if (!g || !X_full || !out_local || D <= 0 || (D % 4) != 0 || ldx < D || ldo < D || (ldx % 4) != 0 || (ldo % 4) != 0)
         return GCA_ERR_INVALID_ARG;
     if (g->row_begin != 0 || g->row_end != g->N) return GCA_ERR_UNSUPPORTED;   // needs dis of every neighbour: full-graph handles only
@@ -66,8 +67,12 @@ extern "C" int gca_propagate(const gca_graph* g, int transpose, const float* X_f
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
         ProfScope ps(transpose ? "propagate_t" : "propagate", st);
-        k_propagate<<<(int)grid, 256, 0, st>>>(transpose ? g->rowptr_t : g->rowptr, transpose ? g->colidx_t : g->colidx, g->dis,
-                                               X_full, ldx, out_local, ldo, n, D, g->row_begin);
+        // forward: rows = targets i (scaled by dst_scale), neighbours = sources j (src_scale); the adjoint walks the CSR by
+        // source: rows = sources, neighbours = targets, the two scales swap roles
+        const float* ss = src_scale ? src_scale : g->dis;
+        const float* ds = dst_scale ? dst_scale : g->dis;
+        k_propagate<<<(int)grid, 256, 0, st>>>(transpose ? g->rowptr_t : g->rowptr, transpose ? g->colidx_t : g->colidx,
+                                               transpose ? ds : ss, transpose ? ss : ds, X_full, ldx, out_local, ldo, n, D);
     }
     GCA_LAUNCH_OK();
     return GCA_OK;

@@ -229,6 +229,9 @@ class GConvAdapter(nn.Module):
 
         # graph structures are shared across adapters / layers / positions through this cache
         self.graph_cache: GraphCache = GLOBAL_GRAPH_CACHE
+        # True: check node ids right after the build (one stream synchronisation per NEW edge_index); "lazy": no
+        # synchronisation - the check result is picked up at a later call (use it when the graph changes every step);
+        # False: never checked (out-of-range ids are then ignored by the build)
         self.validate_edge_index = True
 
     # ------------------------------------------------------------------------------
@@ -264,9 +267,11 @@ class GConvAdapter(nn.Module):
             raise RuntimeError("gconv_adapter_b200.GConvAdapter runs on CUDA (sm_100a) only; there is no CPU path")
         if x.dtype != torch.float32:
             raise RuntimeError("gconv_adapter_b200.GConvAdapter computes in fp32 like the reference; got " + str(x.dtype))
+        if x.dim() == 3 and x.size(0) != 1:
+            # PyG's node_dim = -2: a leading batch dimension shares the graph; the fused normalisation / scalar tail is
+            # row-wise (LayerNorm) or per-call (BatchNorm1d rejects 3-D like the reference's does), so slices are independent
+            return torch.stack([self.forward(x[b], edge_index, edge_attr) for b in range(x.size(0))], dim=0)
         if x.dim() == 3:
-            if x.size(0) != 1:
-                raise RuntimeError("3-D input must be [1, N, hidden] (PyG node_dim=-2 semantics with one graph)")
             x2 = x[0]
         elif x.dim() == 2:
             x2 = x

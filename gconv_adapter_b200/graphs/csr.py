@@ -23,7 +23,7 @@ class GraphStructure:
     (or of one row block ``[row_begin, row_end)`` of it, for the partitioned path)."""
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, normalize: bool = True,
-                 row_begin: int = 0, row_end: Optional[int] = None, validate: bool = True):
+                 row_begin: int = 0, row_end: Optional[int] = None, validate=True):
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError("edge_index must have shape [2, E]")
         if edge_index.dtype != torch.int64:
@@ -53,7 +53,14 @@ class GraphStructure:
                                             self.row_end, int(self.normalize), self.workspace.data_ptr(), nbytes,
                                             stream, C.byref(self._handle)), "gca_graph_build")
             self.nnz = self.nnz_t = None
-            if validate:
+            self._pending = None
+            if validate == "lazy":
+                # no host synchronisation: the flags travel to pinned memory behind the build and are looked at by poll()
+                self._flags_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+                _cabi.check(lib.gca_graph_validate_async(self._handle, self._flags_host.data_ptr(), stream), "gca_graph_validate_async")
+                self._pending = torch.cuda.Event()
+                self._pending.record(torch.cuda.current_stream(self.device))
+            elif validate:
                 self.validate()
 
     # -- lifetime ------------------------------------------------------------------
@@ -69,6 +76,27 @@ class GraphStructure:
     @property
     def handle(self) -> C.c_void_p:
         return self._handle
+
+    def poll(self, wait: bool = False) -> None:
+        """Deferred validation (``validate='lazy'``): once the build has finished on the device, raise if it saw node ids
+        outside [0, N) - the reference fails inside ``index_select`` / ``scatter_add_`` - and learn the hub-row counts.
+        Cheap when nothing is pending; ``wait=True`` blocks until the build is done."""
+        ev = self._pending
+        if ev is None:
+            return
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._pending = None
+        lib = _cabi.load()
+        nnz, nnz_t = C.c_int64(), C.c_int64()
+        st = lib.gca_graph_validate_finish(self._handle, self._flags_host.data_ptr(), C.byref(nnz), C.byref(nnz_t))
+        self.__dict__.pop("_ws_sizes", None)            # hub scratch may have become unnecessary
+        if st == _cabi.GCA_ERR_INDEX_RANGE:
+            raise RuntimeError(f"gconv_adapter_b200: edge_index contains node ids outside [0, {self.num_nodes})")
+        _cabi.check(st, "gca_graph_validate_finish")
+        self.nnz, self.nnz_t = nnz.value, nnz_t.value
 
     def validate(self) -> None:
         """Synchronise and raise on out-of-range node ids (the reference would fail inside
@@ -96,6 +124,8 @@ class GraphStructure:
     def arrays(self) -> dict:
         """Device views of rowptr / colidx / rowptr_t / colidx_t / dis (valid while self lives)."""
         if self.nnz is None:
+            self.poll(wait=True)
+        if self.nnz is None:
             self.validate()
         v = self._view()
         n = self.num_rows
@@ -109,6 +139,8 @@ class GraphStructure:
 
     def edge_coefficients(self) -> torch.Tensor:
         """fp32 ``gcn_norm`` edge weights in forward-CSR order (full-graph handles only)."""
+        if self.nnz is None:
+            self.poll(wait=True)
         if self.nnz is None:
             self.validate()
         out = torch.empty(self.nnz, dtype=torch.float32, device=self.device)
@@ -133,17 +165,27 @@ class GraphCache:
 
     @staticmethod
     def _key(edge_index: torch.Tensor, num_nodes: int, normalize: bool, row_begin: int, row_end: int):
-        return (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()),
+        try:
+            version = edge_index._version
+        except RuntimeError:                 # inference tensors do not track versions
+            return None
+        return (edge_index.data_ptr(), version, tuple(edge_index.shape), tuple(edge_index.stride()),
                 edge_index.device, int(num_nodes), bool(normalize), int(row_begin), int(row_end))
 
     def get(self, edge_index: torch.Tensor, num_nodes: int, normalize: bool = True,
             row_begin: int = 0, row_end: Optional[int] = None, validate: bool = True) -> GraphStructure:
         row_end = num_nodes if row_end is None else row_end
         key = self._key(edge_index, num_nodes, normalize, row_begin, row_end)
+        if key is None:
+            # edge_index was created under torch.inference_mode(): in-place edits cannot be detected, so the structure
+            # is rebuilt on every call (build the graph outside inference_mode, or under no_grad, to get it cached)
+            self.misses += 1
+            return GraphStructure(edge_index, num_nodes, normalize, row_begin, row_end, validate=validate)
         hit = self._entries.get(key)
         if hit is not None:
             self._entries.move_to_end(key)
             self.hits += 1
+            hit[0].poll()
             return hit[0]
         self.misses += 1
         g = GraphStructure(edge_index, num_nodes, normalize, row_begin, row_end, validate=validate)
@@ -151,6 +193,16 @@ class GraphCache:
         while len(self._entries) > self.capacity:
             self._entries.popitem(last=False)
         return g
+
+    def invalidate(self, edge_index: Optional[torch.Tensor] = None) -> None:
+        """Drop the entry built from ``edge_index`` (or everything).  Needed only after writes that do not bump the tensor's
+        version counter (``edge_index.data.copy_()``, custom / DLPack kernels, a collective receiving into the buffer):
+        the cache key is (data_ptr, _version, shape, ...), so such writes would otherwise return the old structure."""
+        if edge_index is None:
+            self._entries.clear()
+            return
+        for key in [k for k, (_, t) in self._entries.items() if t is edge_index or t.data_ptr() == edge_index.data_ptr()]:
+            del self._entries[key]
 
     def clear(self) -> None:
         self._entries.clear()

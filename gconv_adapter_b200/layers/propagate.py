@@ -5,9 +5,11 @@ The two graph transformers of the reference add a normalised-adjacency term next
 * DIFFormer ``gcn_conv(x, edge_index, edge_weight)``  - /root/reference/src/models/transductive/difformer.py:63-79
 * NodeFormer ``add_conv_relational_bias(x, edge_index, b, trans)`` - .../nodeformer.py:202-224
 
-Both build a ``SparseTensor`` with values ``sqrt(1/d[col]) * sqrt(1/d[row])`` (d = in-degree, no self loops added)
-and multiply it head by head.  On the transductive pipeline's graphs - symmetric, exactly one self loop per node
-(scripts/finetune_transductive_learning.py:112-113) - that matrix is the adapter's ``D^-1/2 A' D^-1/2``, so the
+Both build a ``SparseTensor`` with values ``sqrt(1/d_in[col]) * sqrt(1/d[row])`` (no self loops added) and multiply it head
+by head; ``d[row]`` is the IN-degree in ``gcn_conv`` and the OUT-degree in ``add_conv_relational_bias`` - the same thing on
+the undirected graphs of the default pipeline, different on directed ones (``cfg.gnn_baseline.directed`` / ogbn-proteins skip
+``to_undirected``), so the NodeFormer entry passes its own source-side scale.  On graphs with exactly one self loop per node
+(scripts/finetune_transductive_learning.py:112-113) the in-degree matrix is the adapter's ``D^-1/2 A' D^-1/2``, so the
 CSR / CSC / dis arrays the adapters already built for this ``edge_index`` are reused (``GLOBAL_GRAPH_CACHE``) and all
 heads go through ONE d-wide SpMM launch (``gca_propagate``); the backward is the same kernel on the transposed CSR.
 
@@ -34,16 +36,29 @@ def _check_self_loops(graph: GraphStructure, edge_index: torch.Tensor) -> None:
                          "(as scripts/finetune_transductive_learning.py:112-113 produces); got a graph without that")
 
 
+def _out_degree_scale(graph: GraphStructure) -> torch.Tensor:
+    """(out-degree)^-1/2 per node from the CSR by source of the shared handle (cached on the graph object)."""
+    s = getattr(graph, "_out_scale", None)
+    if s is None:
+        rp = graph.arrays()["rowptr_t"]
+        deg = (rp[1:] - rp[:-1]).to(torch.float32)
+        s = (1.0 / deg).sqrt()
+        s = torch.where(torch.isfinite(s), s, torch.zeros_like(s)).contiguous()
+        graph._out_scale = s
+    return s
+
+
 class _Propagate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2d: torch.Tensor, graph: GraphStructure):
+    def forward(ctx, x2d: torch.Tensor, graph: GraphStructure, src_scale):
         lib = _cabi.load()
         x2d = x2d.contiguous()
         out = torch.empty_like(x2d)
         stream = torch.cuda.current_stream(x2d.device).cuda_stream
+        sp = src_scale.data_ptr() if src_scale is not None else None
         _cabi.check(lib.gca_propagate(graph.handle, 0, x2d.data_ptr(), x2d.stride(0), out.data_ptr(), out.stride(0),
-                                      x2d.shape[1], stream), "gca_propagate")
-        ctx.graph = graph
+                                      sp, None, x2d.shape[1], stream), "gca_propagate")
+        ctx.graph, ctx.src_scale = graph, src_scale
         return out
 
     @staticmethod
@@ -52,12 +67,13 @@ class _Propagate(torch.autograd.Function):
         g_out = g_out.contiguous()
         g_in = torch.empty_like(g_out)
         stream = torch.cuda.current_stream(g_out.device).cuda_stream
+        sp = ctx.src_scale.data_ptr() if ctx.src_scale is not None else None
         _cabi.check(lib.gca_propagate(ctx.graph.handle, 1, g_out.data_ptr(), g_out.stride(0), g_in.data_ptr(), g_in.stride(0),
-                                      g_out.shape[1], stream), "gca_propagate")
-        return g_in, None
+                                      sp, None, g_out.shape[1], stream), "gca_propagate")
+        return g_in, None, None
 
 
-def _propagate(x2d: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+def _propagate(x2d: torch.Tensor, edge_index: torch.Tensor, source_out_degree: bool = False) -> torch.Tensor:
     if not x2d.is_cuda:
         raise RuntimeError("gconv_adapter_b200 propagation kernels need CUDA tensors (there is no CPU path)")
     if x2d.dtype != torch.float32:
@@ -66,7 +82,7 @@ def _propagate(x2d: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         raise ValueError("heads * head_dim must be a multiple of 4")
     graph = GLOBAL_GRAPH_CACHE.get(edge_index, x2d.shape[0], True)
     _check_self_loops(graph, edge_index)
-    return _Propagate.apply(x2d, graph)
+    return _Propagate.apply(x2d, graph, _out_degree_scale(graph) if source_out_degree else None)
 
 
 def gcn_conv(x: torch.Tensor, edge_index: torch.Tensor, edge_weight=None) -> torch.Tensor:
@@ -88,5 +104,5 @@ def add_conv_relational_bias(x: torch.Tensor, edge_index: torch.Tensor, b: torch
     bsz, n, h, dd = x.shape
     if bsz != 1:
         raise ValueError("the reference runs the graph transformers with batch size 1 (nodeformer.py:391)")
-    out = _propagate(x.reshape(n, h * dd), edge_index).reshape(1, n, h, dd)
+    out = _propagate(x.reshape(n, h * dd), edge_index, source_out_degree=True).reshape(1, n, h, dd)
     return out * scale.reshape(1, 1, h, 1)

@@ -103,6 +103,11 @@ int    gca_graph_build(const int64_t* src, const int64_t* dst, int64_t E, int32_
 /* Synchronises `stream`; returns GCA_ERR_INDEX_RANGE if an id was out of range, else GCA_OK,
  * and fills nnz / nnz_t (entries of the two CSRs) when the pointers are non-null (host). */
 int    gca_graph_validate(gca_graph* g, gca_stream_t stream, int64_t* nnz, int64_t* nnz_t);
+/* The same without a host synchronisation: _async copies the five flag words into PINNED host memory on `stream`; once an
+ * event the caller recorded after it has completed, _finish (host only) returns what gca_graph_validate would have.
+ * Until then the handle is usable with "hub items unknown": the hop phases then need hub_scratch (gca_hub_scratch_bytes > 0). */
+int    gca_graph_validate_async(const gca_graph* g, int32_t* pinned_host_flags5, gca_stream_t stream);
+int    gca_graph_validate_finish(gca_graph* g, const int32_t* pinned_host_flags5, int64_t* nnz, int64_t* nnz_t);
 void   gca_graph_destroy(gca_graph* g);   /* frees the host descriptor only */
 
 typedef struct gca_graph_view {          /* device pointers into the caller's workspace */
@@ -124,14 +129,16 @@ int    gca_graph_edge_coef(const gca_graph* g, float* coef, gca_stream_t stream)
 size_t gca_hub_scratch_bytes(const gca_graph* g);
 
 /* -------- backbone propagation over the same handle --------
- * out[i, 0:D] = dis[i] * sum_{j in N(i)} dis[j] * X[j, 0:D]  for the handle's local rows; transpose = 1 uses the
- * CSR by source (the adjoint: the backward of transpose = 0).  For a graph that already contains exactly one self loop
- * per node this is DIFFormer's gcn_conv (src/models/transductive/difformer.py:63-79, edge_weight = None) and the
- * aggregation of NodeFormer's add_conv_relational_bias (src/models/transductive/nodeformer.py:202-224) with the heads
- * flattened into D; coefficients differ from the reference's sqrt(1/d) products by <= 2 ULP.  D % 4 == 0; full-graph
- * handles only (row_begin = 0, row_end = N). */
+ * out[i, 0:D] = dst_scale[i] * sum_{j in N(i)} src_scale[j] * X[j, 0:D]  for the handle's rows; transpose = 1 is the adjoint
+ * (walks the CSR by source; the backward of transpose = 0).  NULL scales mean the handle's dis = (in-degree)^-1/2, which for a
+ * graph that already contains exactly one self loop per node is DIFFormer's gcn_conv
+ * (src/models/transductive/difformer.py:63-79, edge_weight = None: both factors use the IN-degree).  NodeFormer's
+ * add_conv_relational_bias (src/models/transductive/nodeformer.py:202-224) scales the source end by the OUT-degree:
+ * pass src_scale[j] = out_degree(j)^-1/2 (they coincide on undirected graphs).  Heads are flattened into D; coefficients
+ * differ from the reference's sqrt(1/d) products by <= 2 ULP.  D % 4 == 0; full-graph handles only. */
 int gca_propagate(const gca_graph* g, int transpose, const float* X_full /*[N,D]*/, int64_t ldx,
-                  float* out_local /*[n,D]*/, int64_t ldo, int32_t D, gca_stream_t stream);
+                  float* out_local /*[n,D]*/, int64_t ldo, const float* src_scale /*[N] or NULL*/,
+                  const float* dst_scale /*[n] or NULL*/, int32_t D, gca_stream_t stream);
 
 /* -------- forward phases (src/finetune/gconv_adapter.py:92-106) --------
  * n = local rows.  *_full buffers hold all N rows (after the caller's all-gather);

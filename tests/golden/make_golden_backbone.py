@@ -28,13 +28,23 @@ def looped(n, e, seed):
     return torch.cat([ei, torch.arange(n, dtype=torch.int64).repeat(2, 1)], dim=1)
 
 
+def directed_looped(n, e, seed):
+    """Directed random graph (each edge in ONE direction only) + one self loop per node: in- and out-degrees differ, which
+    separates gcn_conv (in-degree at both ends) from add_conv_relational_bias (out-degree at the source end)."""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = (src + 1 + torch.randint(0, n - 1, (e,), generator=g)) % n
+    return torch.cat([torch.stack([src, dst]), torch.arange(n, dtype=torch.int64).repeat(2, 1)], dim=1)
+
+
 def main():
     gcn_conv, relbias = backbone_ref.load_reference_functions()
     out_dir = os.path.join(HERE, "backbone")
     os.makedirs(out_dir, exist_ok=True)
-    cases = {"small": (300, 1800, 1, 32, 1), "two_heads": (600, 4000, 2, 32, 2), "wide": (200, 1200, 4, 64, 3)}
+    cases = {"small": (300, 1800, 1, 32, 1), "two_heads": (600, 4000, 2, 32, 2), "wide": (200, 1200, 4, 64, 3),
+             "directed": (400, 2400, 2, 32, 4), "directed_sparse": (500, 700, 1, 64, 5)}
     for name, (n, e, h, dd, seed) in cases.items():
-        ei = looped(n, e, seed)
+        ei = directed_looped(n, e, seed) if name.startswith("directed") else looped(n, e, seed)
         gen = torch.Generator().manual_seed(100 + seed)
         x = torch.randn(n, h, dd, generator=gen)
         g_out = torch.randn(n, h, dd, generator=gen)

@@ -1,0 +1,127 @@
+"""Boundary robustness on the GPU (SURVEY.md section 8b "Threading"): one graph handle shared by two
+streams at once, one process driving two devices, deferred validation, cache invalidation, inference-mode tensors and
+batched 3-D inputs."""
+import pytest
+import torch
+
+from gconv_adapter_b200 import GConvAdapter, GraphCache, GraphStructure
+from gconv_adapter_b200.graphs.synthetic import make_graph, make_inputs, symmetric_random_graph
+
+from util import load_module_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _module(d, r, params, dev="cuda:0", **kw):
+    m = GConvAdapter(d, r, learnable_scalar=True, **kw)
+    load_module_params(m, params)
+    m = m.to(dev)
+    m.graph_cache = GraphCache()
+    return m
+
+
+def _fwd_bwd(m, x, ei, g):
+    for p in m.parameters():
+        p.grad = None
+    xx = x.clone().requires_grad_(True)
+    y = m(xx, ei)
+    y.backward(g)
+    return [y.detach(), xx.grad] + [p.grad for p in m.parameters()]
+
+
+def test_one_handle_two_streams_at_once():
+    """The handle is read-only after the build: every scratch byte is per call.  Two adapters (hub rows included: a star)
+    run forward + backward on two streams over the SAME handle, many times, interleaved by the hardware; every result must
+    equal the serial one bit for bit."""
+    n, d, r = 30000, 256, 16
+    hub = torch.zeros(4000, dtype=torch.int64)
+    leaves = torch.arange(1, 4001, dtype=torch.int64)
+    ei = torch.cat([symmetric_random_graph(n, 200000, seed=3), torch.stack([hub, leaves]), torch.stack([leaves, hub])], 1).cuda()
+    xa, ga, params = make_inputs(n, d, r, seed=1)
+    xb, gb, _ = make_inputs(n, d, r, seed=2)
+    xa, ga, xb, gb = (t.cuda() for t in (xa, ga, xb, gb))
+    ma, mb = _module(d, r, params), _module(d, r, params)
+    shared = GraphCache()
+    ma.graph_cache = mb.graph_cache = shared
+    ref_a, ref_b = _fwd_bwd(ma, xa, ei, ga), _fwd_bwd(mb, xb, ei, gb)
+    assert shared.misses == 1 and shared.hits >= 1               # one build, one handle for both
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(5):
+        with torch.cuda.stream(sa):
+            out_a = _fwd_bwd(ma, xa, ei, ga)
+        with torch.cuda.stream(sb):
+            out_b = _fwd_bwd(mb, xb, ei, gb)
+        torch.cuda.synchronize()
+        for got, want in zip(out_a, ref_a):
+            assert torch.equal(got, want)
+        for got, want in zip(out_b, ref_b):
+            assert torch.equal(got, want)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process (gpurun --gpus 2)")
+def test_one_process_two_devices():
+    """Shared-memory opt-ins and SM counts are remembered per device: the same kernels must launch on cuda:1 after cuda:0."""
+    ei, n = make_graph("arxiv", seed=0, scale=0.1)
+    x, g, params = make_inputs(n, 256, 16, seed=4)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        m = _module(256, 16, params, dev)
+        outs.append([t.cpu() for t in _fwd_bwd(m, x.to(dev), ei.to(dev), g.to(dev))])
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
+
+
+def test_lazy_validation_needs_no_sync_and_still_raises():
+    n = 5000
+    ei = symmetric_random_graph(n, 30000, seed=5).cuda()
+    g = GraphStructure(ei, n, True, validate="lazy")
+    assert g.nnz is None and g._pending is not None               # nothing was waited for
+    x, go, params = make_inputs(n, 64, 16, seed=6)
+    m = _module(64, 16, params)
+    m.validate_edge_index = "lazy"
+    want = _fwd_bwd(_module(64, 16, params), x.cuda(), ei, go.cuda())
+    got = _fwd_bwd(m, x.cuda(), ei, go.cuda())                    # runs with "hub items unknown" (per-call hub scratch)
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    m.graph_for(ei, n)                                            # cache hit: picks the finished check up
+    assert m.graph_cache.get(ei, n, True, validate="lazy").nnz == 30000 + n
+    bad = ei.clone()
+    bad[0, 7] = n + 3
+    gb = GraphStructure(bad, n, True, validate="lazy")
+    with pytest.raises(RuntimeError, match="outside"):
+        gb.poll(wait=True)
+
+
+def test_cache_invalidate_and_inference_mode_tensors():
+    n = 3000
+    ei = symmetric_random_graph(n, 20000, seed=7).cuda()
+    cache = GraphCache()
+    g1 = cache.get(ei, n)
+    ei.data.copy_(symmetric_random_graph(n, 20000, seed=8).cuda())   # a write that does NOT bump ei._version
+    assert cache.get(ei, n) is g1                                  # ... is invisible to the cache key
+    cache.invalidate(ei)
+    g2 = cache.get(ei, n)
+    assert g2 is not g1
+    with torch.inference_mode():
+        ei_inf = symmetric_random_graph(n, 20000, seed=8).cuda()
+        x, _, params = make_inputs(n, 64, 16, seed=9)
+        m = _module(64, 16, params)
+        y = m(x.cuda(), ei_inf)                                   # _version is unavailable: rebuilt, not crashed
+        y2 = m(x.cuda(), ei)
+    assert torch.equal(y, y2)
+
+
+def test_batched_three_d_input_shares_the_graph():
+    n, d, r = 2000, 64, 16
+    ei = symmetric_random_graph(n, 12000, seed=10).cuda()
+    _, _, params = make_inputs(n, d, r, seed=11)
+    m = _module(d, r, params)
+    xb = torch.randn(3, n, d, device="cuda")
+    yb = m(xb, ei)
+    assert yb.shape == xb.shape
+    for b in range(3):
+        assert torch.equal(yb[b], m(xb[b], ei))
