@@ -383,6 +383,29 @@ def run_host_workload(args, lib, dev):
     torch.cuda.synchronize()
     ad_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - c0)) / args.steps
 
+    graphed_ms = None
+    if name != "molecules":
+        # static graph: forward and backward of every adapter as one CUDA graph each (gconv_adapter_b200.graphed_adapter)
+        from gconv_adapter_b200 import graphed_adapter
+        fs = [graphed_adapter(a, xs[0], dev_pool[0][1]) for a in adapters]
+
+        def graphed_step():
+            h = xs[0]
+            for f in fs:
+                h = f(h)
+            h.sum().backward()
+
+        for _ in range(5):
+            graphed_step()
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        t0.record()
+        for _ in range(args.steps):
+            graphed_step()
+        t1.record()
+        torch.cuda.synchronize()
+        graphed_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - c0)) / args.steps
+
     line = {
         "metric": METRIC, "value": e_step * calls / (ms_step / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -392,7 +415,8 @@ def run_host_workload(args, lib, dev):
                    "l2": "working set fits L2; no flush (latency-bound config: host issue time is what is measured)",
                    "parallelism": "1 GPU"},
         "adapter_only": {"ms_per_step": ad_ms, "adapter_calls_per_step": calls, "ms_per_adapter_fwd_bwd": ad_ms / calls,
-                         "value": e_step * calls / (ad_ms / 1e3), "unit": UNIT},
+                         "value": e_step * calls / (ad_ms / 1e3), "unit": UNIT,
+                         "cuda_graph_ms_per_adapter_fwd_bwd": (graphed_ms / calls) if graphed_ms else None},
         "e2e": {"value": e_step * calls / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks,

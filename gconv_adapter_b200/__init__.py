@@ -5,9 +5,10 @@ Drop-in for ``src.finetune.gconv_adapter.GConvAdapter`` of PanPapag/GConv-Adapte
 signature; the arithmetic runs in hand-written CUDA kernels behind the C ABI of include/gca.h.
 """
 from .finetune.gconv_adapter import GConvAdapter
+from .graphed import graphed_adapter
 from .graphs.csr import GLOBAL_GRAPH_CACHE, GraphCache, GraphStructure
 
-__all__ = ["GConvAdapter", "GraphStructure", "GraphCache", "GLOBAL_GRAPH_CACHE", "install_reference_alias"]
+__all__ = ["GConvAdapter", "GraphStructure", "GraphCache", "GLOBAL_GRAPH_CACHE", "graphed_adapter", "install_reference_alias"]
 __version__ = "0.1.0"
 
 
