@@ -50,15 +50,17 @@ def _out_degree_scale(graph: GraphStructure) -> torch.Tensor:
 
 class _Propagate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2d: torch.Tensor, graph: GraphStructure, src_scale):
+    def forward(ctx, x2d: torch.Tensor, graph: GraphStructure, src_scale=None, dst_scale=None):
+        """out[i] = dst_scale[i] * sum_j src_scale[j] * x[j]  (None = the handle's in-degree^-1/2)."""
         lib = _cabi.load()
         x2d = x2d.contiguous()
         out = torch.empty_like(x2d)
         stream = torch.cuda.current_stream(x2d.device).cuda_stream
         sp = src_scale.data_ptr() if src_scale is not None else None
+        dp = dst_scale.data_ptr() if dst_scale is not None else None
         _cabi.check(lib.gca_propagate(graph.handle, 0, x2d.data_ptr(), x2d.stride(0), out.data_ptr(), out.stride(0),
-                                      sp, None, x2d.shape[1], stream), "gca_propagate")
-        ctx.graph, ctx.src_scale = graph, src_scale
+                                      sp, dp, x2d.shape[1], stream), "gca_propagate")
+        ctx.graph, ctx.src_scale, ctx.dst_scale = graph, src_scale, dst_scale
         return out
 
     @staticmethod
@@ -68,9 +70,10 @@ class _Propagate(torch.autograd.Function):
         g_in = torch.empty_like(g_out)
         stream = torch.cuda.current_stream(g_out.device).cuda_stream
         sp = ctx.src_scale.data_ptr() if ctx.src_scale is not None else None
+        dp = ctx.dst_scale.data_ptr() if ctx.dst_scale is not None else None
         _cabi.check(lib.gca_propagate(ctx.graph.handle, 1, g_out.data_ptr(), g_out.stride(0), g_in.data_ptr(), g_in.stride(0),
-                                      sp, None, g_out.shape[1], stream), "gca_propagate")
-        return g_in, None, None
+                                      sp, dp, g_out.shape[1], stream), "gca_propagate")
+        return g_in, None, None, None
 
 
 def _propagate(x2d: torch.Tensor, edge_index: torch.Tensor, source_out_degree: bool = False) -> torch.Tensor:
