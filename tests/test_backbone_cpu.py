@@ -9,7 +9,8 @@ import torch
 
 from oracle import backbone_ref
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backbone", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backbone", "*.npz"))
+              if not os.path.basename(p).startswith("mol_"))     # mol_*: the molecular layers (tests/test_*molecular*.py)
 
 
 def _load(path):

@@ -14,7 +14,8 @@ from oracle import backbone_ref
 from util import assert_close
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backbone", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backbone", "*.npz"))
+              if not os.path.basename(p).startswith("mol_"))     # mol_*: the molecular layers (tests/test_*molecular*.py)
 
 
 def _load(path):
