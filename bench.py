@@ -90,6 +90,8 @@ def algorithmic_bytes(n, e_prime, d, r):
         # split K3 (operand >> L2, e.g. products-shaped): plain hop kernel + expand-only kernel
         "hop_plain_fwd": 2 * nr + idx + dis, "hop_plain_bwd": 2 * nr + idx + dis,
         "expand_fwd": nr + 2 * nd, "expand_bwd": nr + 2 * nd,
+        "bwd_up": nd + 2 * nr + dis,                  # gY (once) -> gH2' and the gWu / gbu partials
+        "expand_wgrad_bwd": 3 * nd + nr,              # gY, X (once each), gP -> gX, gWd partials, <gY, X>
     }
     total = 28 * n * d + 52 * n * r + 16 * e_prime + 32 * n
     return per, total

@@ -156,10 +156,22 @@ extern "C" int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full, con
     const PdlHint pdl_hint(n);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Scratch S = scratch_ptrs(scratch, d, r);
+    const bool want_dot = skip && scalar;
+    if (n > 0 && skip && gX && r == 16 && d % 32 == 0 && d <= 256 && n >= 2048) {
+        // One pass over gY and X: plain r-wide hop for gP, then gX = gP Wd + s gY, the gWd partials and <gY, X> together
+        // (gY and X cross HBM once each instead of twice).  Falls through to K3 + K4 when the streaming kernel declines.
+        const Csr c = csr_of(g, true, hub_scratch);
+        GCA_TRY(launch_hop(r, false, c, gH1p_full, nullptr, GCA_ACT_NONE, nullptr, nullptr, gP_local, nullptr, nullptr, nullptr, n, st,
+                           1, "hop_plain_bwd"));
+        const int s2 = launch_expand_wgrad(r, X, ldx, gY, ldg, gP_local, Wd, scalar, gX, ldgx, S.gd, want_dot ? S.dot : nullptr,
+                                           S.header, 1, n, d, st);
+        if (s2 == GCA_OK) return GCA_OK;
+        if (s2 != GCA_ERR_UNSUPPORTED) return s2;
+        // (gP is already in place; the register-fed path below recomputes it inside K3 - correct, only slower)
+    }
     GCA_TRY(launch_hop_expand(r, false, csr_of(g, true, hub_scratch), gH1p_full, Wd, nullptr, gY, ldg, scalar, 0, skip ? 1 : 0,
                               gP_local, gX, ldgx, n, d, st));
     if (n == 0) return GCA_OK;
-    const bool want_dot = skip && scalar;
     return wgrad_any(r, X, ldx, gP_local, want_dot ? gY : nullptr, ldg, S.gd, nullptr, want_dot ? S.dot : nullptr, S.header, 1,
                      n, d, st);
 }
@@ -175,7 +187,7 @@ extern "C" int gca_bwd_finalize(const void* scratch, const float* Wu, const floa
 // ---------------- single-GPU conveniences ----------------
 // forward workspace: [P' scratch | hub scratch]; backward workspace: [gH2' | gH1' | gP | partial-sum scratch | hub scratch]
 namespace {
-inline size_t rw_bytes(int n, int r) { return align_up(sizeof(float) * (size_t)(n > 0 ? n : 1) * r); }
+inline size_t rw_bytes(int n, int r) { return align_up(sizeof(float) * (size_t)(n > 0 ? n + (n & 1) : 2) * r); }   // even row count
 }
 
 extern "C" size_t gca_forward_workspace_bytes(const gca_graph* g, int32_t d, int32_t r) {

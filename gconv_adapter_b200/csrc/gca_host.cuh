@@ -118,6 +118,11 @@ struct DenseStreamArgs {
     const char* prof_name;
 };
 int launch_dense_stream(int r, const DenseStreamArgs& a, cudaStream_t st);
+// gX = gP Wd + s gY, gWd partials = gP^T X and <gY, X> in one pass over gY and X (gca_stream_bwd.cu; gP from a plain hop).
+// Returns GCA_ERR_UNSUPPORTED for shapes it does not cover (callers fall back to K3 + K4).
+int launch_expand_wgrad(int r, const float* X, int64_t ldx, const float* gY, int64_t ldg, const float* gP, const float* Wd,
+                        const float* scalar, float* gX, int64_t ldgx, float* partG, float* partDot, int* header, int slot,
+                        int n, int d, cudaStream_t st);
 // K6
 int launch_finalize(const Scratch& S, const float* Wu, const float* bu, const float* scalar, int skip, float* gWd, float* gbd,
                     float* gWu, float* gbu, float* gscalar, int d, int r, cudaStream_t st);

@@ -248,7 +248,7 @@ class _PartitionedFunction(torch.autograd.Function):
         g_y = g_y.contiguous()
         bufs = comm.buffers(world * s, r, dev, ("gh2", "gh1"))
         gh2_full, gh1_full = bufs["gh2"], bufs["gh1"]
-        gp = torch.empty((max(n, 1), r), dtype=torch.float32, device=dev)
+        gp = torch.empty((max(n + (n & 1), 2), r), dtype=torch.float32, device=dev)     # even row count (gca_bwd_hop1_down)
         need_x = ctx.needs_input_grad[0]
         g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if need_x else None
         # parameter gradients of this rank's rows, packed for ONE all-reduce

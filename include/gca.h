@@ -178,7 +178,10 @@ int gca_bwd_hop2(const gca_graph* g, const float* gH2p_full /*[N,r]*/, const flo
                  const float* H1_local /*NULL unless silu*/, int act, float* gH1p_local /*[n,r]*/,
                  void* scratch, void* hub_scratch, const gca_push* push, int32_t r, gca_stream_t stream);
 /* gP[j] = dis[j] * sum_{i in out(j)} gH1'[i] ; gX = gP Wd [+ s * gY] ; partials for gWd = gP^T X
- * and for <gY, X> (needed by gscalar).  gX may be NULL (x does not require grad). */
+ * and for <gY, X> (needed by gscalar).  gX may be NULL (x does not require grad).
+ * With skip, gX, r = 16, d % 32 == 0, d <= 256, n >= 2048 this is a plain hop + ONE streaming pass over gY and X
+ * (gca_stream_bwd.cu).  gP_local must be readable for an EVEN number of rows (n rounded up; contents of the pad row are
+ * ignored): at r = 16 the pass reads it through a [ceil(n / 2), 32]-float tensor map. */
 int gca_bwd_hop1_down(const gca_graph* g, const float* gH1p_full /*[N,r]*/, const float* X, int64_t ldx,
                       const float* gY, int64_t ldg, const float* Wd, const float* scalar, int skip,
                       float* gP_local /*[n,r] workspace*/, float* gX, int64_t ldgx,

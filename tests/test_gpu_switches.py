@@ -13,7 +13,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GCA_VARS = ("GCA_DISABLE_TC", "GCA_DISABLE_STREAM", "GCA_DISABLE_TMA", "GCA_DISABLE_PDL", "GCA_SPLIT_MB", "GCA_STREAM_TF32")
+GCA_VARS = ("GCA_DISABLE_TC", "GCA_DISABLE_STREAM", "GCA_DISABLE_TMA", "GCA_DISABLE_PDL", "GCA_SPLIT_MB", "GCA_STREAM_TF32",
+            "GCA_DISABLE_BWD_FUSE")
 
 
 def run_case(case: str, env_over: dict) -> dict:
@@ -27,10 +28,14 @@ def run_case(case: str, env_over: dict) -> dict:
 
 # switch setting -> {phase: variant} that must be reported (r = 16 case / r = 32 case where they differ)
 SETTINGS = {
-    "default": ({}, {"project_fwd": "stream_f16", "bwd_up": "stream_f16", "wgrad_down": "stream_f16", "hop_expand_fwd": "tcgen05",
-                     "hop_expand_bwd": "tcgen05"}),
-    "split_k3": ({"GCA_SPLIT_MB": "0"}, {"hop_plain_fwd": "", "expand_fwd": "tcgen05", "hop_plain_bwd": "", "expand_bwd": "tcgen05"}),
-    "stream_tf32": ({"GCA_STREAM_TF32": "1"}, {"project_fwd": "stream_tf32", "bwd_up": "stream_tf32", "wgrad_down": "stream_tf32"}),
+    "default": ({}, {"project_fwd": "stream_f16", "bwd_up": "stream_f16", "hop_expand_fwd": "tcgen05", "hop_plain_bwd": "",
+                     "expand_wgrad_bwd": "stream_f16"}),
+    "no_bwd_fuse": ({"GCA_DISABLE_BWD_FUSE": "1"}, {"project_fwd": "stream_f16", "bwd_up": "stream_f16", "wgrad_down": "stream_f16",
+                                                    "hop_expand_fwd": "tcgen05", "hop_expand_bwd": "tcgen05"}),
+    "split_k3": ({"GCA_SPLIT_MB": "0", "GCA_DISABLE_BWD_FUSE": "1"},
+                 {"hop_plain_fwd": "", "expand_fwd": "tcgen05", "hop_plain_bwd": "", "expand_bwd": "tcgen05"}),
+    "stream_tf32": ({"GCA_STREAM_TF32": "1"}, {"project_fwd": "stream_tf32", "bwd_up": "stream_tf32", "wgrad_down": "stream_tf32",
+                                               "hop_expand_bwd": "tcgen05"}),
     "no_stream": ({"GCA_DISABLE_STREAM": "1"}, {"project_fwd": "mma", "project_bwd": "mma", "wgrad_up": "mma", "wgrad_down": "mma",
                                                 "hop_expand_fwd": "tcgen05"}),
     "no_tma": ({"GCA_DISABLE_TMA": "1"}, {"project_fwd": "mma", "wgrad_up": "mma", "hop_expand_fwd": "mma", "hop_expand_bwd": "mma"}),
