@@ -144,16 +144,15 @@ __device__ __forceinline__ float4 hub_row_sum(const float* __restrict__ hub_part
 // One CSR row per lane group (R/4 lanes); every lane of the warp must call this.
 // Rows up to kLongRow neighbours: the group walks them alone.  Up to kHubDeg: the whole warp sweeps the row
 // (fixed shuffle tree).  Longer ("hub") rows: their partial sums were produced by k_hub_partials, one warp per
-// kHubChunk neighbours, and are only added up here.
+// kHubChunk neighbours, and are only added up here.  warp_spmm_range takes the row's [beg, end) from the caller, so a
+// kernel that loops over row batches can fetch the next batch's row header while the current one gathers.
 template <int R>
-__device__ __forceinline__ float4 warp_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                                 const float* __restrict__ F, int row, bool valid, int lane,
-                                                 const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
+__device__ __forceinline__ float4 warp_spmm_range(const int* __restrict__ colidx, const float* __restrict__ F, int row, int beg,
+                                                  int end, int lane, const int* __restrict__ hubitem,
+                                                  const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     const int sub = lane % LPG, grp = lane / LPG;
-    int beg = 0, end = 0;
-    if (valid) { beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
-    const int deg = end - beg;
+    const int deg = end - beg;                           // 0 for lanes without a row
     const bool is_hub = deg > kHubDeg;
     const bool is_long = deg > kLongRow && !is_hub;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -172,6 +171,14 @@ __device__ __forceinline__ float4 warp_spmm_rows(const int* __restrict__ rowptr,
         if (grp == g) acc = part;
     }
     return acc;
+}
+template <int R>
+__device__ __forceinline__ float4 warp_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                 const float* __restrict__ F, int row, bool valid, int lane,
+                                                 const int* __restrict__ hubitem, const float* __restrict__ hub_part) {
+    int beg = 0, end = 0;
+    if (valid) { beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1); }
+    return warp_spmm_range<R>(colidx, F, row, beg, end, lane, hubitem, hub_part);
 }
 
 __device__ __forceinline__ float act_apply(float h, int act) {

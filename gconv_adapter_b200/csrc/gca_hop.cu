@@ -53,6 +53,15 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPG, grp = lane / LPG;
     const int wglobal = blockIdx.x * (blockDim.x >> 5) + warp, wtotal = gridDim.x * (blockDim.x >> 5);
+    // row header (rowptr pair + dis) of the NEXT batch is fetched while the current one gathers: two of the four dependent
+    // memory round trips of a batch leave the critical path.  The first header is read before the dependency wait: the
+    // graph arrays were written by the build, which completed before the kernel preceding this one started.
+    int nbeg = 0, nend = 0;
+    float ndi = 0.f;
+    {
+        const int row0 = wglobal * GPW + grp;
+        if (row0 < n) { nbeg = __ldg(rowptr + row0); nend = __ldg(rowptr + row0 + 1); ndi = __ldg(dis + row0); }
+    }
     pdl_wait();
     pdl_trigger();
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -61,9 +70,15 @@ k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const floa
     for (int rowbase = wglobal * GPW; rowbase < n; rowbase += wtotal * GPW) {
         const int row = rowbase + grp;
         const bool valid = row < n;
-        const float4 acc = warp_spmm_rows<R>(rowptr, colidx, F, row, valid, lane, hubitem, hub_part);
+        const int beg = nbeg, end = nend;
+        const float di = ndi;
+        {
+            const int nrow = row + wtotal * GPW;
+            nbeg = nend = 0;
+            if (nrow < n) { nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1); ndi = __ldg(dis + nrow); }
+        }
+        const float4 acc = warp_spmm_range<R>(colidx, F, row, beg, end, lane, hubitem, hub_part);
         if (!valid) continue;
-        const float di = __ldg(dis + row);
         const size_t o = (size_t)row * R + sub * 4;
         if (!BWD) {
             if (plain) {                                   // just the hop: out = dis * (A' F)  (first half of a split K3)
