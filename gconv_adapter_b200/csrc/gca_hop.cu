@@ -43,7 +43,7 @@ k_hub_partials(const int* __restrict__ rowptr, const int* __restrict__ colidx, c
 //                      BWD:  gH1'[j] = dis[j] * act'(.) * dis[j] * sum_i F[i]   (+ per-CTA sum for gbd)
 // ------------------------------------------------------------------------------------------
 template <int R, bool BWD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)   // 5 CTAs / SM = 48 registers: the gather wants warps, not registers
 k_hop(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ dis,
       const float* __restrict__ F, const float* __restrict__ bias, int act,
       const float* __restrict__ Zp_saved, const float* __restrict__ H1_saved,

@@ -31,6 +31,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 from typing import Optional
 
 import torch
@@ -313,6 +314,7 @@ class PartitionedGConvAdapter(GConvAdapter):
         self._comm = None
         self._comm_key = None
         self._graphs: dict = {}
+        self._captured: list = []
 
     def _graph(self, edge_index: torch.Tensor, num_nodes: int, lo: int, hi: int):
         key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), num_nodes, lo, hi, self.normalize)
@@ -341,8 +343,53 @@ class PartitionedGConvAdapter(GConvAdapter):
             self._comm_key = key
         return self._comm
 
+    def capture_step(self, step_fn):
+        """Capture ``step_fn`` - one training step on STATIC tensors: zero/None the grads, ``y = self(x, ei, N)``,
+        ``y.backward(g)`` - in a CUDA graph and return its ``replay`` callable, or None if any rank could not capture
+        (the ranks agree, then all stay eager).  With the peer-memory exchange no library collective sits inside a step
+        (pushes ride in the producing kernels, barriers and the all-reduce are libgca kernels), so the whole forward +
+        backward of every rank is one graph launch.  Collective: every rank calls it at the same point.  The graph is
+        owned by the module and destroyed by ``close()`` before the peer arena is unmapped.  Drop every reference to
+        outputs / losses of earlier eager steps first: a live autograd graph keeps AccumulateGrad nodes bound to the
+        stream they were created on, which invalidates a capture on another stream."""
+        if self._comm is None:
+            step_fn()                                   # builds the graph handle, the arena and the comm
+        if not getattr(self._comm, "fused_push", False):
+            return None                                 # NCCL inside the step: left to eager launches
+        group, dev = self.process_group, torch.cuda.current_device()
+        ok, graph = 1, None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):               # warm-up on a non-default stream, as capture will run
+                step_fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            dist.barrier(group)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_fn()
+            torch.cuda.synchronize()
+        except Exception as ex:      # noqa: BLE001 - any capture problem means "run eagerly", on every rank
+            ok = 0
+            warnings.warn(f"CUDA-graph capture of the partitioned step failed ({type(ex).__name__}: {ex}); eager launches")
+        flag = torch.tensor([ok], device=torch.device("cuda", dev))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if flag.item() == 0:
+            return None
+        self._captured.append(graph)
+        graph.replay()
+        torch.cuda.synchronize()
+        return graph.replay
+
     def close(self) -> None:
-        """Unmap the peer arena (collective: call on every rank, before destroy_process_group)."""
+        """Destroy captured steps and unmap the peer arena (collective: call on every rank, before
+        destroy_process_group)."""
+        if self._captured:
+            torch.cuda.synchronize()
+            for g in self._captured:
+                g.reset()
+            self._captured.clear()
         if self._comm is not None and hasattr(self._comm, "close"):
             self._comm.close()
         self._comm, self._comm_key = None, None

@@ -226,6 +226,28 @@ int gca_peer_export(void* ptr, void* handle64 /* host out */);
 int gca_peer_open(const void* handle64 /* host */, void** ptr /* host out */);
 int gca_peer_close(void* ptr);
 
+/* -------- multi-GPU for a client that owns an NCCL communicator --------
+ * The whole partitioned forward / backward of ONE rank: the phases above with an in-place ncclAllGather of each r-wide
+ * operand between them and an ncclAllReduce (sum) of the parameter gradients at the end, all on `stream`.
+ * nccl_comm is the caller's ncclComm_t (as void*), world / rank its size and this caller's rank; g must cover this rank's
+ * block of ceil(N / world) rows (row_begin = rank * ceil(N / world)).  X, Y, gY, gX, Zp_save, H1_save, H2_save are the
+ * LOCAL rows.  libgca does not link NCCL: ncclAllGather / ncclAllReduce / ncclGroupStart / ncclGroupEnd are resolved at
+ * first use from the NCCL already loaded in the process ("libnccl.so.2" by soname, or the file named by GCA_NCCL_LIB);
+ * gca_nccl_available() tells whether that worked (GCA_ERR_UNSUPPORTED otherwise; world = 1 never needs it).
+ * On an NVLink box the peer-memory exchange above (gca_push + gca_peer_barrier) is the faster path. */
+int    gca_nccl_available(void);
+size_t gca_forward_nccl_workspace_bytes(const gca_graph* g, int32_t world, int32_t d, int32_t r);
+int    gca_forward_nccl(const gca_graph* g, void* nccl_comm, int32_t world, int32_t rank, const float* X, int64_t ldx,
+                        const float* Wd, const float* bd, const float* Wu, const float* bu, const float* scalar,
+                        int act, int skip, void* workspace, float* Zp_save, float* H1_save /*NULL unless silu*/,
+                        float* H2_save, float* Y, int64_t ldy, int32_t d, int32_t r, gca_stream_t stream);
+size_t gca_backward_nccl_workspace_bytes(const gca_graph* g, int32_t world, int32_t d, int32_t r);
+int    gca_backward_nccl(const gca_graph* g, void* nccl_comm, int32_t world, int32_t rank, const float* gY, int64_t ldg,
+                         const float* X, int64_t ldx, const float* Zp_save, const float* H1_save, const float* H2_save,
+                         const float* Wd, const float* Wu, const float* bu, const float* scalar, int act, int skip,
+                         void* workspace, float* gX, int64_t ldgx, float* gWd, float* gbd, float* gWu, float* gbu,
+                         float* gscalar, int32_t d, int32_t r, gca_stream_t stream);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t gca_launch_count(void);
 /* Per-kernel device timing for bench.py's roofline: while enabled, every launch is bracketed by

@@ -1,6 +1,7 @@
 """Target program for ncu: one arxiv-shaped (BASELINE.json configs[3]) adapter forward + backward
-after the graph build and two warm-up steps.  Kernel launch order per step:
-project_fwd, hop_fwd, hop_expand_fwd | project_bwd, wgrad_up, hop_bwd, hop_expand_bwd, wgrad_down, finalize."""
+after the graph build and two warm-up steps.  Kernel launch order per step (round 2, r = 16):
+project_fwd, hop_fwd, hop_expand_fwd | bwd_up, hop_bwd, hop_plain_bwd, expand_wgrad_bwd, finalize.
+(round 1: ... | project_bwd, wgrad_up, hop_bwd, hop_expand_bwd, wgrad_down, finalize.)"""
 import os
 import sys
 

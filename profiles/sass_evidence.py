@@ -1,15 +1,19 @@
 """Count the SASS mnemonics that prove which hardware paths each libgca kernel uses (B200_PROFILING.md: tcgen05.mma ->
 UTCHMMA, tcgen05.commit -> UTCBAR, tcgen05.ld -> LDTM, cp.async.bulk.tensor -> UTMALDG / UTMASTG, cp.async.bulk ->
-UBLKCP, mbarrier -> SYNCS, mma.sync tf32 -> HMMA.1688.F32.TF32).   python profiles/sass_evidence.py > profiles/r1_sass_evidence.md"""
+UBLKCP, mbarrier -> SYNCS, mma.sync tf32 -> HMMA.1688.F32.TF32, mma.sync f16 (the scaled 2xFP16 split) -> HMMA.16816.F32,
+movmatrix -> MOVM, multi-GPU barrier -> ST/LD .STRONG.SYS).   python profiles/sass_evidence.py > profiles/r2_sass_evidence.md"""
 import collections
 import re
 import subprocess
 import sys
 
-lib = sys.argv[1] if len(sys.argv) > 1 else "gconv_adapter_b200/lib/libgca.so"
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from gconv_adapter_b200.build import lib_path  # noqa: E402
+
+lib = sys.argv[1] if len(sys.argv) > 1 else lib_path()
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-pat = re.compile(r"\b(UTCHMMA|UTCBAR|LDTM|UTMALDG|UTMASTG|UBLKCP|SYNCS|HMMA\.1688\.F32\.TF32|FFMA)\b")
-keys = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "HMMA.1688.F32.TF32", "FFMA"]
+pat = re.compile(r"\b(UTCHMMA|UTCBAR|LDTM|UTMALDG|UTMASTG|UBLKCP|SYNCS|HMMA\.1688\.F32\.TF32|HMMA\.16816\.F32|MOVM|FFMA)\b")
+keys = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "HMMA.1688.F32.TF32", "HMMA.16816.F32", "MOVM", "FFMA"]
 cnt, cur = collections.OrderedDict(), None
 for ln in sass.splitlines():
     m = re.search(r"Function : (\S+)", ln)

@@ -1,7 +1,8 @@
 """Turn `ncu --page raw --csv` output of one adapter step into a per-kernel summary (markdown + traffic.json).
 
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv
-    python profiles/summarize_ncu.py raw.csv arxiv profiles/r1_step_summary.md
+    python profiles/summarize_ncu.py raw.csv arxiv profiles/r2_step_ncu_full.md
+The capture must hold exactly the kernels of ONE step (8 launches in round 2, 9 in round 1).
 """
 import csv
 import json
@@ -28,9 +29,11 @@ def scale(r, key, want):
     return v * f.get(u, 1)
 
 
-ORDER = ["project_fwd", "hop_fwd", "hop_expand_fwd", "project_bwd", "wgrad_up", "hop_bwd", "hop_expand_bwd", "wgrad_down", "finalize"]
-lines = ["| # | phase | kernel | time (us) | DRAM read (MB) | DRAM write (MB) | DRAM % peak | tensor pipe % | warps active % | regs |",
-         "|---|---|---|---|---|---|---|---|---|---|"]
+ORDER_R1 = ["project_fwd", "hop_fwd", "hop_expand_fwd", "project_bwd", "wgrad_up", "hop_bwd", "hop_expand_bwd", "wgrad_down", "finalize"]
+ORDER_R2 = ["project_fwd", "hop_fwd", "hop_expand_fwd", "bwd_up", "hop_bwd", "hop_plain_bwd", "expand_wgrad_bwd", "finalize"]
+ORDER = ORDER_R2 if len(data) == len(ORDER_R2) else ORDER_R1
+lines = ["| # | phase | kernel | time (us) | DRAM read (MB) | DRAM write (MB) | DRAM % peak | tensor pipe % | issue active % | warps active % | regs |",
+         "|---|---|---|---|---|---|---|---|---|---|---|"]
 traffic = {}
 for i, r in enumerate(data):
     name = r[ci["Kernel Name"]]
@@ -42,6 +45,7 @@ for i, r in enumerate(data):
     lines.append(f"| {i} | {phase} | `{short}` | {t:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | "
                  f"{val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                  f"{val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                 f"{val(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
                  f"{val(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {val(r, 'launch__registers_per_thread'):.0f} |")
 open(out_md, "w").write("\n".join(lines) + "\n")
 tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")

@@ -133,6 +133,30 @@ def _rank_worker(rank, world, port, n, d, r, comm, out):
                 for k in cur["grads"]:
                     assert torch.equal(cur["grads"][k], res["grads"][k]), k
             res = cur
+        # the same step captured in ONE CUDA graph by the module (peer exchange only) replays the same bits
+        part.DEBUG_KEEP_SAVED = False
+        part.LAST_SAVED.clear()
+        del y, xl            # a live output keeps the eager autograd graph (and its default-stream AccumulateGrad nodes) alive
+        xs = x[lo:hi].cuda().requires_grad_(True)
+        held = {}
+
+        def step():
+            for p_ in m.parameters():
+                p_.grad = None
+            xs.grad = None
+            ys = m(xs, eid, n)
+            ys.backward(gl)
+            held["y"] = ys.detach()
+
+        replay = m.capture_step(step)
+        assert (replay is not None) == (comm == "peer")
+        if replay is not None:
+            for _ in range(3):
+                replay()
+            torch.cuda.synchronize()
+            assert torch.equal(held["y"].cpu(), res["y"]) and torch.equal(xs.grad.cpu(), res["gx"])
+            for k, p_ in m.named_parameters():
+                assert torch.equal(p_.grad.cpu(), res["grads"][k]), k
         out[rank] = res
         m.close()
     finally:
@@ -173,3 +197,113 @@ def test_multi_gpu_run_matches_oracle(world, comm):
             assert_close(out[rank]["grads"][k], gr[k], f"{comm}: grad {k} on rank {rank}", noise_floor=floor)
             if comm == "peer":                    # summed in rank order on every GPU: identical bits everywhere
                 assert torch.equal(out[rank]["grads"][k], out[0]["grads"][k]), k
+
+
+# ---- the C-ABI entries that take the client's own ncclComm_t (include/gca.h, gca_nccl.cu) ----
+def _nccl_lib():
+    import ctypes as C
+    lib = C.CDLL("libnccl.so.2")          # by soname: the copy torch already loaded
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_byte * 128)]
+
+    lib.ncclGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    lib.ncclCommDestroy.argtypes = [C.c_void_p]
+    return lib, UniqueId
+
+
+def _nccl_abi_worker(rank, world, port, n, d, r, act_name, out):
+    import ctypes as C
+    import torch.distributed as dist
+    from gconv_adapter_b200 import GConvAdapter, _cabi
+    from gconv_adapter_b200.graphs.csr import GraphCache, GraphStructure
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # rendezvous only: the data path is the raw communicator
+    comm = C.c_void_p()
+    nccl = None
+    try:
+        nccl, UniqueId = _nccl_lib()
+        uid = UniqueId()
+        if rank == 0:
+            assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+        box = [bytes(uid.internal)]
+        dist.broadcast_object_list(box, src=0)
+        C.memmove(uid.internal, box[0], 128)
+        assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+
+        lib = _cabi.load()
+        assert lib.gca_nccl_available() == 1
+        dev = torch.device("cuda", rank)
+        ei = symmetric_random_graph(n, 8 * n, seed=41)
+        x, g_out, params = make_inputs(n, d, r, seed=42)
+        lo, hi = row_block(n, world, rank)
+        nl = hi - lo
+        eid = ei.to(dev)
+        graph = GraphStructure(eid, n, True, lo, hi)
+        act = {"relu": 1, "silu": 2}[act_name]
+        P = {k: v.to(dev).contiguous() for k, v in params.items()}
+        xl, gl = x[lo:hi].to(dev).contiguous(), g_out[lo:hi].to(dev).contiguous()
+        st = torch.cuda.current_stream().cuda_stream
+        f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        ws_f = torch.empty(lib.gca_forward_nccl_workspace_bytes(graph.handle, world, d, r), dtype=torch.uint8, device=dev)
+        ws_b = torch.empty(lib.gca_backward_nccl_workspace_bytes(graph.handle, world, d, r), dtype=torch.uint8, device=dev)
+        zp, h1, h2, y = f32(nl, r), f32(nl, r), f32(nl, r), f32(nl, d)
+        gx, gwd, gbd, gwu, gbu, gs = f32(nl, d), f32(r, d), f32(r), f32(d, r), f32(d), f32(1)
+        for _ in range(2):        # twice: workspaces are reusable, results repeat bit for bit
+            _cabi.check(lib.gca_forward_nccl(graph.handle, comm, world, rank, xl.data_ptr(), d, P["conv_down.lin.weight"].data_ptr(),
+                                             P["conv_down.bias"].data_ptr(), P["conv_up.lin.weight"].data_ptr(),
+                                             P["conv_up.bias"].data_ptr(), P["scalar"].data_ptr(), act, 1, ws_f.data_ptr(),
+                                             zp.data_ptr(), h1.data_ptr(), h2.data_ptr(), y.data_ptr(), d, d, r, st), "gca_forward_nccl")
+            _cabi.check(lib.gca_backward_nccl(graph.handle, comm, world, rank, gl.data_ptr(), d, xl.data_ptr(), d, zp.data_ptr(),
+                                              h1.data_ptr(), h2.data_ptr(), P["conv_down.lin.weight"].data_ptr(),
+                                              P["conv_up.lin.weight"].data_ptr(), P["conv_up.bias"].data_ptr(), P["scalar"].data_ptr(),
+                                              act, 1, ws_b.data_ptr(), gx.data_ptr(), d, gwd.data_ptr(), gbd.data_ptr(), gwu.data_ptr(),
+                                              gbu.data_ptr(), gs.data_ptr(), d, r, st), "gca_backward_nccl")
+            torch.cuda.synchronize()
+        # the 1-GPU module on the full inputs, on this rank's GPU
+        ref = GConvAdapter(d, r, non_linearity=act_name, learnable_scalar=True)
+        load_module_params(ref, params)
+        ref = ref.to(dev)
+        ref.graph_cache = GraphCache()
+        xf = x.to(dev).requires_grad_(True)
+        yr = ref(xf, eid)
+        yr.backward(g_out.to(dev))
+        torch.cuda.synchronize()
+        # same kernels, same per-row arithmetic; only the tile alignment of a shard (power-of-two box scales) may differ
+        rel = lambda a, b: ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
+        assert rel(y, yr.detach()[lo:hi]) <= 2e-6, "Y rows differ from the 1-GPU module"
+        assert rel(gx, xf.grad[lo:hi]) <= 2e-6, "gX rows differ from the 1-GPU module"
+        got = {"conv_down.lin.weight": gwd, "conv_down.bias": gbd, "conv_up.lin.weight": gwu, "conv_up.bias": gbu, "scalar": gs}
+        worst = 0.0
+        for k, p_ in ref.named_parameters():
+            err = (got[k].double() - p_.grad.double()).abs().max().item() / max(p_.grad.double().abs().max().item(), 1e-30)
+            worst = max(worst, err if k != "scalar" else 0.0)
+            if k == "scalar":       # heavily cancelling sum: fp32 noise floor as in tests/test_gpu_adapter.py::compare
+                floor = 5e-7 * float((g_out.abs().double() * yr.detach().cpu().abs().double()).sum()) / abs(float(params["scalar"]))
+                assert abs(float(got[k]) - float(p_.grad)) <= 1e-5 * abs(float(p_.grad)) + floor
+        assert worst <= 1e-5, worst
+        out[rank] = worst
+        del graph
+    finally:
+        if nccl is not None and comm.value:
+            nccl.ncclCommDestroy(comm)
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("act", ["relu", "silu"])
+def test_nccl_comm_entry_points_match_single_gpu(act):
+    """gca_forward_nccl / gca_backward_nccl driven by a raw ncclComm_t created through ctypes (no torch.distributed on the
+    data path): Y and gX rows within 2e-6 of the 1-GPU module (same kernels), summed parameter gradients within 1e-5."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_abi_worker, args=(2, port, 30001, 256, 16, act, out), nprocs=2, join=True)
+    assert len(out) == 2
