@@ -93,6 +93,9 @@ def algorithmic_bytes(n, e_prime, d, r):
         "bwd_up": nd + 2 * nr + dis,                  # gY (once) -> gH2' and the gWu / gbu partials
         "expand_wgrad_bwd": 3 * nd + nr,              # gY, X (once each), gP -> gX, gWd partials, <gY, X>
     }
+    # small graphs: ONE cooperative kernel per direction (gca_small.cu) = the sum of the phases it replaces
+    per["small_fwd"] = per["project_fwd"] + per["hop_fwd"] + per["hop_expand_fwd"]
+    per["small_bwd"] = per["bwd_up"] + per["hop_bwd"] + per["hop_plain_bwd"] + per["expand_wgrad_bwd"]
     total = 28 * n * d + 52 * n * r + 16 * e_prime + 32 * n
     return per, total
 

@@ -106,7 +106,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------
 // sparse row gather
 // ------------------------------------------------------------------------------------------
-template <int R>
+// CG: the operand was written earlier in the SAME kernel (fused small-graph kernels): coherent L2 loads instead of the
+// read-only path.
+template <int R, bool CG = false>
 __device__ __forceinline__ float4 gather_rows(const float* __restrict__ F, const int* __restrict__ colidx,
                                               int beg, int end, int stride, int sub) {
     // Batches of 8 neighbours: all 8 index loads are issued together, then all 8 row loads, so a row of
@@ -119,7 +121,9 @@ __device__ __forceinline__ float4 gather_rows(const float* __restrict__ F, const
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            v[u] = (j[u] >= 0) ? ldg4(F + (size_t)j[u] * R + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u] = (j[u] < 0) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                   : CG   ? __ldcg(reinterpret_cast<const float4*>(F + (size_t)j[u] * R + sub * 4))
+                          : ldg4(F + (size_t)j[u] * R + sub * 4);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
     }
@@ -146,18 +150,19 @@ __device__ __forceinline__ float4 hub_row_sum(const float* __restrict__ hub_part
 // (fixed shuffle tree).  Longer ("hub") rows: their partial sums were produced by k_hub_partials, one warp per
 // kHubChunk neighbours, and are only added up here.  warp_spmm_range takes the row's [beg, end) from the caller, so a
 // kernel that loops over row batches can fetch the next batch's row header while the current one gathers.
-template <int R>
+// hubitem == nullptr: no pre-reduced hub partials exist, rows of any length are swept by the warp.
+template <int R, bool CG = false>
 __device__ __forceinline__ float4 warp_spmm_range(const int* __restrict__ colidx, const float* __restrict__ F, int row, int beg,
                                                   int end, int lane, const int* __restrict__ hubitem,
                                                   const float* __restrict__ hub_part) {
     constexpr int LPG = R / 4, GPW = 32 / LPG;
     const int sub = lane % LPG, grp = lane / LPG;
     const int deg = end - beg;                           // 0 for lanes without a row
-    const bool is_hub = deg > kHubDeg;
+    const bool is_hub = hubitem != nullptr && deg > kHubDeg;
     const bool is_long = deg > kLongRow && !is_hub;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (is_hub) acc = hub_row_sum<R>(hub_part, __ldg(hubitem + row), (deg + kHubChunk - 1) / kHubChunk, sub);
-    else if (!is_long) acc = gather_rows<R>(F, colidx, beg, end, 1, sub);
+    else if (!is_long) acc = gather_rows<R, CG>(F, colidx, beg, end, 1, sub);
     unsigned longmask = __ballot_sync(0xffffffffu, is_long);
     while (longmask) {                                   // warp-uniform
         const int src = __ffs(longmask) - 1;
@@ -165,7 +170,7 @@ __device__ __forceinline__ float4 warp_spmm_range(const int* __restrict__ colidx
         const unsigned gm = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << (g * LPG));
         longmask &= ~gm;
         const int b = __shfl_sync(0xffffffffu, beg, src), e = __shfl_sync(0xffffffffu, end, src);
-        float4 part = gather_rows<R>(F, colidx, b + grp, e, GPW, sub);
+        float4 part = gather_rows<R, CG>(F, colidx, b + grp, e, GPW, sub);
 #pragma unroll
         for (int off = LPG; off < 32; off <<= 1) part = f4_add(part, f4_shfl_xor(part, off));
         if (grp == g) acc = part;

@@ -118,6 +118,16 @@ struct DenseStreamArgs {
     const char* prof_name;
 };
 int launch_dense_stream(int r, const DenseStreamArgs& a, cudaStream_t st);
+// Fused small-graph path (gca_small.cu): the whole forward / backward of a full-graph handle as ONE cooperative kernel
+// each, for n <= 4096, n d <= 2^19, r d <= 8192 (GCA_DISABLE_SMALL=1 switches it off).
+bool small_path_ok(const gca_graph* g, int d, int r);
+int small_forward(const gca_graph* g, const float* X, int64_t ldx, const float* Wd, const float* bd, const float* Wu,
+                  const float* bu, const float* scalar, int act, int skip, float* P, float* Zp, float* H1, float* H2, float* Y,
+                  int64_t ldy, int d, int r, cudaStream_t st);
+int small_backward(const gca_graph* g, const float* gY, int64_t ldg, const float* X, int64_t ldx, const float* Zp,
+                   const float* H1, const float* H2, const float* Wd, const float* Wu, const float* bu, const float* scalar,
+                   int act, int skip, float* gH2, float* gH1, float* gP, float* gX, int64_t ldgx, const Scratch& S, float* gWd,
+                   float* gbd, float* gWu, float* gbu, float* gscalar, int d, int r, cudaStream_t st);
 // gX = gP Wd + s gY, gWd partials = gP^T X and <gY, X> in one pass over gY and X (gca_stream_bwd.cu; gP from a plain hop).
 // Returns GCA_ERR_UNSUPPORTED for shapes it does not cover (callers fall back to K3 + K4).
 int launch_expand_wgrad(int r, const float* X, int64_t ldx, const float* gY, int64_t ldg, const float* gP, const float* Wd,

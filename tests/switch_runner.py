@@ -23,6 +23,12 @@ CASES = {
     "arxiv_silu": ("arxiv", 0.25, 256, 16, {"non_linearity": "silu"}),
     "products64_relu": ("products", 1 / 64, 256, 32, {}),
     "products64_silu_noskip": ("products", 1 / 64, 256, 32, {"non_linearity": "silu", "skip_connection": False}),
+    # small graphs: the fused one-kernel-per-direction path (gca_small.cu) unless GCA_DISABLE_SMALL=1
+    "cora_relu": ("cora", 1.0, 64, 8, {}),
+    "cora_silu_noskip": ("cora", 1.5, 64, 16, {"non_linearity": "silu", "skip_connection": False}),
+    "molecules_relu": ("molecules", 1.0, 300, 16, {}),
+    "small_r32_noscalar": ("cora", 1.0, 128, 32, {"learnable_scalar": False}),
+    "small_r64_unnormalized": ("cora", 0.5, 64, 64, {"normalize": False}),
 }
 
 

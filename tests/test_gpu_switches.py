@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GCA_VARS = ("GCA_DISABLE_TC", "GCA_DISABLE_STREAM", "GCA_DISABLE_TMA", "GCA_DISABLE_PDL", "GCA_SPLIT_MB", "GCA_STREAM_TF32",
-            "GCA_DISABLE_BWD_FUSE")
+            "GCA_DISABLE_BWD_FUSE", "GCA_DISABLE_SMALL")
 
 
 def run_case(case: str, env_over: dict) -> dict:
@@ -78,3 +78,24 @@ def test_switch_parity_rank32(setting, case):
     assert out["ok"]
     for phase, variant in expect.items():
         assert out["variants"].get(phase) == variant, f"{setting}: {phase} ran as {out['variants'].get(phase)!r}, all: {out['variants']}"
+
+
+SMALL_CASES = ["cora_relu", "cora_silu_noskip", "molecules_relu", "small_r32_noscalar", "small_r64_unnormalized"]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_small_graph_fused_path(case):
+    """cora / molecule-batch sized graphs (n <= 4096) run the whole forward and the whole backward as ONE cooperative
+    kernel each (gca_small.cu): parity against the oracle, and nothing else was launched."""
+    out = run_case(case, {})
+    assert out["ok"]
+    assert out["variants"] == {"small_fwd": "fused", "small_bwd": "fused"}, out["variants"]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_small_graph_through_the_phase_kernels(case):
+    """GCA_DISABLE_SMALL=1: the same graphs through the per-phase kernels (the path they took before the fused one)."""
+    out = run_case(case, {"GCA_DISABLE_SMALL": "1"})
+    assert out["ok"]
+    assert "small_fwd" not in out["variants"] and "small_bwd" not in out["variants"], out["variants"]
+    assert "finalize" in out["variants"]
