@@ -45,6 +45,21 @@ def _sizes(lib, graph: GraphStructure, d: int, r: int):
     return hit
 
 
+def _raw_stream(dev: torch.device) -> int:
+    """Make ``dev`` current (libgca launches on the current device) and return its current stream's handle.  The public
+    ``torch.cuda.current_stream().cuda_stream`` costs ~10 us per call in Python bookkeeping - a fifth of a tiny-graph
+    step (profiles/r2_host_profile.txt) - so the raw accessors are used when this torch build has them."""
+    idx = dev.index
+    try:
+        if torch._C._cuda_getDevice() != idx:
+            torch.cuda.set_device(idx)
+        return torch._C._cuda_getCurrentRawStream(idx)
+    except AttributeError:
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
+        return torch.cuda.current_stream().cuda_stream
+
+
 def _align(nbytes: int) -> int:
     return (nbytes + 255) // 256 * 256
 
@@ -61,9 +76,7 @@ class _GConvAdapterFunction(torch.autograd.Function):
         n, d = x.shape
         r = w_down.shape[0]
         dev = x.device
-        if torch.cuda.current_device() != dev.index:
-            torch.cuda.set_device(dev)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _raw_stream(dev)
         if not w_down.is_contiguous():
             w_down = w_down.contiguous()
         if not w_up.is_contiguous():
@@ -107,9 +120,7 @@ class _GConvAdapterFunction(torch.autograd.Function):
         dev = x.device
         if g_y.stride(-1) != 1 or g_y.stride(0) % 4 != 0 or g_y.data_ptr() % 16 != 0:
             g_y = g_y.contiguous()
-        if torch.cuda.current_device() != dev.index:
-            torch.cuda.set_device(dev)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _raw_stream(dev)
         rw = ctx.rw
         base = buf.data_ptr()
         zp_ptr, h2_ptr = base, base + rw

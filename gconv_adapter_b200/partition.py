@@ -337,7 +337,21 @@ class PartitionedGConvAdapter(GConvAdapter):
         if self._comm is None or self._comm_key != key:
             self.close()
             if choice == "peer" and dist.get_world_size(self.process_group) > 1:
-                self._comm = PeerMemoryComm(num_nodes, self.hidden_size, self.bottleneck_size, self.process_group, device)
+                # mapping the peers' arenas can fail (no peer access between two GPUs, IPC disabled in a container):
+                # the ranks agree, and all of them take the torch.distributed exchange instead
+                comm, ok = None, 1
+                try:
+                    comm = PeerMemoryComm(num_nodes, self.hidden_size, self.bottleneck_size, self.process_group, device)
+                except Exception as ex:      # noqa: BLE001 - any set-up problem means "use the collectives", on every rank
+                    ok = 0
+                    warnings.warn(f"NVLink peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using torch.distributed collectives")
+                flag = torch.tensor([ok], device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.process_group)
+                if flag.item() == 0:
+                    if comm is not None:
+                        comm.close()
+                    comm = CollectiveComm(self.process_group)
+                self._comm = comm
             else:
                 self._comm = CollectiveComm(self.process_group)
             self._comm_key = key

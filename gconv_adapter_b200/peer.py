@@ -46,25 +46,42 @@ class PeerGroup:
             self.off_regions.append(off)
             off += _align(int(nb))
         self.nbytes = off
+        # Every rank goes through the same two collectives (handle exchange, status exchange) whatever fails locally,
+        # so a rank whose allocation / export / mapping fails cannot leave the others stuck in one of them.
         with torch.cuda.device(self.device):
             own = C.c_void_p()
-            _cabi.check(self.lib.gca_peer_alloc(self.nbytes, C.byref(own)), "gca_peer_alloc")
             handle = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
-            _cabi.check(self.lib.gca_peer_export(own, handle), "gca_peer_export")
+            self._own, self.ptrs, self._opened, self._closed = own, [], [], False
+            err: Optional[Exception] = None
+            try:
+                _cabi.check(self.lib.gca_peer_alloc(self.nbytes, C.byref(own)), "gca_peer_alloc")
+                _cabi.check(self.lib.gca_peer_export(own, handle), "gca_peer_export")
+            except Exception as ex:      # noqa: BLE001 - reported after the collectives below
+                err = ex
             handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            self._own = own
-            self.ptrs: list[int] = []
-            self._opened: list[C.c_void_p] = []
-            for h in range(self.world):
-                if h == self.rank:
-                    self.ptrs.append(own.value)
-                    continue
-                p = C.c_void_p()
-                _cabi.check(self.lib.gca_peer_open(handles[h], C.byref(p)), "gca_peer_open (CUDA IPC between the GPUs of one node)")
-                self._opened.append(p)
-                self.ptrs.append(p.value)
-            dist.barrier(group)          # every arena is allocated, zeroed and mapped before anyone signals through it
+            dist.all_gather_object(handles, None if err else handle.raw, group=group)
+            if err is None and any(h is None for h in handles):
+                err = RuntimeError("a peer could not allocate / export its arena")
+            if err is None:
+                try:
+                    for h in range(self.world):
+                        if h == self.rank:
+                            self.ptrs.append(own.value)
+                            continue
+                        p = C.c_void_p()
+                        _cabi.check(self.lib.gca_peer_open(handles[h], C.byref(p)),
+                                    "gca_peer_open (CUDA IPC between the GPUs of one node)")
+                        self._opened.append(p)
+                        self.ptrs.append(p.value)
+                except Exception as ex:  # noqa: BLE001
+                    err = ex
+            oks = [None] * self.world    # every arena is allocated, zeroed and mapped before anyone signals through it
+            dist.all_gather_object(oks, err is None, group=group)
+            if err is None and not all(oks):
+                err = RuntimeError(f"peer arena set-up failed on rank(s) {[k for k, o in enumerate(oks) if not o]}")
+            if err is not None:
+                self.close()
+                raise err
         self.sync = _cabi.PeerSync()
         self.sync.world, self.sync.rank = self.world, self.rank
         for h in range(self.world):
