@@ -209,7 +209,7 @@ extern "C" int gca_forward(const gca_graph* g, const float* X, int64_t ldx, cons
     // small graphs: one cooperative kernel for the whole forward (anything it cannot take goes through the phases,
     // which also report argument errors)
     if (X && Wd && bd && Wu && bu && Zp_save && H2_save && Y && ldx >= d && ldy >= d && act >= GCA_ACT_NONE &&
-        act <= GCA_ACT_SILU && (act != GCA_ACT_SILU || H1_save) && small_path_ok(g, d, r))
+        act <= GCA_ACT_SILU && (act != GCA_ACT_SILU || H1_save) && small_path_ok(g, d, r, static_cast<cudaStream_t>(stream)))
         return small_forward(g, X, ldx, Wd, bd, Wu, bu, scalar, act, skip, Pp, Zp_save, H1_save, H2_save, Y, ldy, d, r,
                              static_cast<cudaStream_t>(stream));
     GCA_TRY(gca_fwd_project(g, X, ldx, Wd, Pp, nullptr, d, r, stream));
@@ -238,7 +238,7 @@ extern "C" int gca_backward(const gca_graph* g, const float* gY, int64_t ldg, co
     void* scratch = b + 3 * rw;
     void* hub = hub_scratch_bytes(g) ? b + 3 * rw + gca_bwd_scratch_bytes(d, r) : nullptr;
     if (gY && X && Zp_save && H2_save && Wd && Wu && bu && ldg >= d && ldx >= d && (!gX || ldgx >= d) && act >= GCA_ACT_NONE &&
-        act <= GCA_ACT_SILU && (act != GCA_ACT_SILU || H1_save) && small_path_ok(g, d, r))
+        act <= GCA_ACT_SILU && (act != GCA_ACT_SILU || H1_save) && small_path_ok(g, d, r, static_cast<cudaStream_t>(stream)))
         return small_backward(g, gY, ldg, X, ldx, Zp_save, H1_save, H2_save, Wd, Wu, bu, scalar, act, skip, gH2p, gH1p, gP, gX,
                               ldgx, scratch_ptrs(scratch, d, r), gWd, gbd, gWu, gbu, gscalar, d, r,
                               static_cast<cudaStream_t>(stream));

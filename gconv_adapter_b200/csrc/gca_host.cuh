@@ -119,8 +119,8 @@ struct DenseStreamArgs {
 };
 int launch_dense_stream(int r, const DenseStreamArgs& a, cudaStream_t st);
 // Fused small-graph path (gca_small.cu): the whole forward / backward of a full-graph handle as ONE cooperative kernel
-// each, for n <= 4096, n d <= 2^19, r d <= 8192 (GCA_DISABLE_SMALL=1 switches it off).
-bool small_path_ok(const gca_graph* g, int d, int r);
+// each, for n <= 4096, n d <= 2^19, r d <= 8192, on a stream that is not being captured (GCA_DISABLE_SMALL=1 switches it off).
+bool small_path_ok(const gca_graph* g, int d, int r, cudaStream_t st);
 int small_forward(const gca_graph* g, const float* X, int64_t ldx, const float* Wd, const float* bd, const float* Wu,
                   const float* bu, const float* scalar, int act, int skip, float* P, float* Zp, float* H1, float* H2, float* Y,
                   int64_t ldy, int d, int r, cudaStream_t st);

@@ -502,10 +502,17 @@ int small_backward_t(SmallBwd a, cudaStream_t st) {
 
 }  // namespace
 
-bool small_path_ok(const gca_graph* g, int d, int r) {
+bool small_path_ok(const gca_graph* g, int d, int r, cudaStream_t st) {
     const int n = g->row_end - g->row_begin;
-    return small_enabled() && g->row_begin == 0 && g->row_end == g->N && n > 0 && n <= kSmallMaxRows &&
-           (int64_t)n * d <= kSmallMaxElems && r * d <= kSmallMaxRD && shape_ok(d, r);
+    if (!(small_enabled() && g->row_begin == 0 && g->row_end == g->N && n > 0 && n <= kSmallMaxRows &&
+          (int64_t)n * d <= kSmallMaxElems && r * d <= kSmallMaxRD && shape_ok(d, r)))
+        return false;
+    // What the fused kernels save is host time (2 launches instead of 8).  Inside a CUDA graph launches cost nothing and the
+    // eight phase kernels, overlapped by programmatic dependent launch, replay FASTER (51 vs 56 us per cora-shaped step,
+    // profiles/README.md R2-4): a capturing stream takes the phases.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return cap == cudaStreamCaptureStatusNone;
 }
 
 int small_forward(const gca_graph* g, const float* X, int64_t ldx, const float* Wd, const float* bd, const float* Wu,
