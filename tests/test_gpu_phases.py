@@ -120,3 +120,57 @@ def test_backward_dense_phases_match_fp64(n, d, r, with_scalar):
     run()
     for a, b in zip(keep, (gh2, g_wd, g_wu, g_bu, gx)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,d,r,act", [(30001, 256, 16, 1), (3000, 64, 8, 2), (20011, 128, 32, 1)])
+def test_nccl_entry_points_with_world_one_equal_the_single_gpu_calls(n, d, r, act):
+    """gca_forward_nccl / gca_backward_nccl with world = 1 (no communicator needed) run the same phases as gca_forward /
+    gca_backward on their own workspace layout: identical bits.  (The 2-GPU run with a raw ncclComm_t is in
+    tests/test_gpu_partition.py.)"""
+    lib = _cabi.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(n + d + r)
+    ei = symmetric_random_graph(n, 6 * n, seed=n).to(dev)
+    graph = GraphStructure(ei, n, True)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)
+    x, gy = rnd(n, d), rnd(n, d)
+    wd, bd, wu, bu, sc = rnd(r, d) * 0.05, rnd(r) * 0.05, rnd(d, r) * 0.05, rnd(d) * 0.05, torch.tensor([1.3], device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    u8 = lambda nb: torch.empty(max(int(nb), 256), device=dev, dtype=torch.uint8)
+    outs = []
+    for nccl in (False, True):
+        zp, h1, h2, y = f32(n, r), f32(n, r), f32(n, r), f32(n, d)
+        gx, gwd, gbd, gwu, gbu, gs = f32(n, d), f32(r, d), f32(r), f32(d, r), f32(d), f32(1)
+        if nccl:
+            wf = u8(lib.gca_forward_nccl_workspace_bytes(graph.handle, 1, d, r))
+            wb = u8(lib.gca_backward_nccl_workspace_bytes(graph.handle, 1, d, r))
+            _cabi.check(lib.gca_forward_nccl(graph.handle, None, 1, 0, x.data_ptr(), d, wd.data_ptr(), bd.data_ptr(), wu.data_ptr(),
+                                             bu.data_ptr(), sc.data_ptr(), act, 1, wf.data_ptr(), zp.data_ptr(), h1.data_ptr(),
+                                             h2.data_ptr(), y.data_ptr(), d, d, r, st), "gca_forward_nccl")
+            _cabi.check(lib.gca_backward_nccl(graph.handle, None, 1, 0, gy.data_ptr(), d, x.data_ptr(), d, zp.data_ptr(),
+                                              h1.data_ptr(), h2.data_ptr(), wd.data_ptr(), wu.data_ptr(), bu.data_ptr(),
+                                              sc.data_ptr(), act, 1, wb.data_ptr(), gx.data_ptr(), d, gwd.data_ptr(),
+                                              gbd.data_ptr(), gwu.data_ptr(), gbu.data_ptr(), gs.data_ptr(), d, r, st),
+                        "gca_backward_nccl")
+        else:
+            os.environ.pop("GCA_DISABLE_SMALL", None)
+            wf = u8(lib.gca_forward_workspace_bytes(graph.handle, d, r))
+            wb = u8(lib.gca_backward_workspace_bytes(graph.handle, d, r))
+            _cabi.check(lib.gca_forward(graph.handle, x.data_ptr(), d, wd.data_ptr(), bd.data_ptr(), wu.data_ptr(), bu.data_ptr(),
+                                        sc.data_ptr(), act, 1, wf.data_ptr(), zp.data_ptr(), h1.data_ptr(), h2.data_ptr(),
+                                        y.data_ptr(), d, d, r, st), "gca_forward")
+            _cabi.check(lib.gca_backward(graph.handle, gy.data_ptr(), d, x.data_ptr(), d, zp.data_ptr(), h1.data_ptr(), h2.data_ptr(),
+                                         wd.data_ptr(), wu.data_ptr(), bu.data_ptr(), sc.data_ptr(), act, 1, wb.data_ptr(),
+                                         gx.data_ptr(), d, gwd.data_ptr(), gbd.data_ptr(), gwu.data_ptr(), gbu.data_ptr(),
+                                         gs.data_ptr(), d, r, st), "gca_backward")
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (y, gx, gwd, gbd, gwu, gbu, gs)])
+    names = ("y", "gx", "gwd", "gbd", "gwu", "gbu", "gs")
+    small = n <= 4096        # gca_forward takes the fused small-graph kernels there, the nccl entry the phase kernels
+    for k, a, b in zip(names, outs[0], outs[1]):
+        if small:
+            tol = 1e-5 * float(a.abs().max()) + (5e-7 * float((gy.abs().double() * outs[0][0].abs().double()).sum()) / 1.3 if k == "gs" else 0.0)
+            assert float((a.double() - b.double()).abs().max()) <= tol, k
+        else:
+            assert torch.equal(a, b), k

@@ -80,7 +80,7 @@ def test_switch_parity_rank32(setting, case):
         assert out["variants"].get(phase) == variant, f"{setting}: {phase} ran as {out['variants'].get(phase)!r}, all: {out['variants']}"
 
 
-SMALL_CASES = ["cora_relu", "cora_silu_noskip", "molecules_relu", "small_r32_noscalar", "small_r64_unnormalized"]
+SMALL_CASES = ["cora_relu", "cora_silu_noskip", "molecules_relu", "small_r32_noscalar", "small_r64_unnormalized", "small_powerlaw"]
 
 
 @pytest.mark.parametrize("case", SMALL_CASES)
@@ -90,6 +90,8 @@ def test_small_graph_fused_path(case):
     out = run_case(case, {})
     assert out["ok"]
     assert out["variants"] == {"small_fwd": "fused", "small_bwd": "fused"}, out["variants"]
+    if case == "small_powerlaw":
+        assert out["max_in_degree"] > 512, out["max_in_degree"]      # the case really has hub rows
 
 
 @pytest.mark.parametrize("case", SMALL_CASES)
