@@ -86,6 +86,9 @@ SIGNATURES = {
     "gca_peer_export": (C.c_int, [_f, C.c_char_p]),
     "gca_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "gca_peer_close": (C.c_int, [_f]),
+    "gca_layernorm_scratch_bytes": (_sz, [_i32]),
+    "gca_layernorm_scale_fwd": (C.c_int, [_f, _i64, _f, _f, _f, C.c_float, _f, _i64, _f, _f, _i32, _i32, _f]),
+    "gca_layernorm_scale_bwd": (C.c_int, [_f, _i64, _f, _i64, _f, _f, _f, _f, _f, _f, _i64, _f, _f, _f, _f, _i32, _i32, _f]),
     "gca_nccl_available": (C.c_int, []),
     "gca_forward_nccl_workspace_bytes": (_sz, [_f, _i32, _i32, _i32]),
     "gca_forward_nccl": (C.c_int, [_f, _f, _i32, _i32, _f, _i64, _f, _f, _f, _f, _f, C.c_int, C.c_int, _f, _f, _f, _f, _f, _i64,

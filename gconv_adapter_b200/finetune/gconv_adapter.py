@@ -13,6 +13,7 @@ a CPU tensor, or a missing libgca.so, raises ``RuntimeError``.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -143,6 +144,55 @@ class _GConvAdapterFunction(torch.autograd.Function):
         return g_x, g_wd, g_bd, g_wu, g_bu, g_s, None, None, None
 
 
+class _LayerNormScaleFunction(torch.autograd.Function):
+    """``LayerNorm(x) * scalar`` (gconv_adapter.py:98-106 with normalization='layer_norm') as one pass forward and one
+    pass backward over ``[N, d]`` (gca_layernorm.cu) instead of the stock LayerNorm + mul kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, scalar, eps: float):
+        lib = _cabi.load()
+        if x.stride(-1) != 1 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:
+            x = x.contiguous()
+        n, d = x.shape
+        dev = x.device
+        stream = _raw_stream(dev)
+        y = torch.empty((n, d), dtype=torch.float32, device=dev)
+        stats = torch.empty((2, max(n, 1)), dtype=torch.float32, device=dev)
+        weight = weight.contiguous() if weight is not None else None
+        bias = bias.contiguous() if bias is not None else None
+        _cabi.check(lib.gca_layernorm_scale_fwd(x.data_ptr(), x.stride(0), _ptr(weight), _ptr(bias), _ptr(scalar), float(eps),
+                                                y.data_ptr(), y.stride(0), stats[0].data_ptr(), stats[1].data_ptr(), n, d,
+                                                stream), "gca_layernorm_scale_fwd")
+        ctx.has = (weight is not None, bias is not None, scalar is not None)
+        ctx.save_for_backward(x, stats, *[t for t in (weight, bias, scalar) if t is not None])
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        lib = _cabi.load()
+        saved = list(ctx.saved_tensors)
+        x, stats = saved[0], saved[1]
+        rest = saved[2:]
+        weight = rest.pop(0) if ctx.has[0] else None
+        bias = rest.pop(0) if ctx.has[1] else None
+        scalar = rest.pop(0) if ctx.has[2] else None
+        n, d = x.shape
+        dev = x.device
+        if g_y.stride(-1) != 1 or g_y.stride(0) % 4 != 0 or g_y.data_ptr() % 16 != 0:
+            g_y = g_y.contiguous()
+        stream = _raw_stream(dev)
+        g_x = torch.empty((n, d), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        g_w = torch.empty((d,), dtype=torch.float32, device=dev) if weight is not None else None
+        g_b = torch.empty((d,), dtype=torch.float32, device=dev) if bias is not None else None
+        g_s = torch.empty((1,), dtype=torch.float32, device=dev) if scalar is not None else None
+        ws = torch.empty(lib.gca_layernorm_scratch_bytes(d), dtype=torch.uint8, device=dev)
+        _cabi.check(lib.gca_layernorm_scale_bwd(g_y.data_ptr(), g_y.stride(0), x.data_ptr(), x.stride(0), _ptr(weight),
+                                                _ptr(bias), _ptr(scalar), stats[0].data_ptr(), stats[1].data_ptr(), _ptr(g_x),
+                                                g_x.stride(0) if g_x is not None else d, _ptr(g_w), _ptr(g_b), _ptr(g_s),
+                                                ws.data_ptr(), n, d, stream), "gca_layernorm_scale_bwd")
+        return g_x, g_w, g_b, g_s, None
+
+
 class _Lin(nn.Module):
     """Holds ``lin.weight`` [out, in] exactly where PyG's ``GCNConv.lin`` (bias-free Linear) has it."""
 
@@ -244,6 +294,7 @@ class GConvAdapter(nn.Module):
         # synchronisation - the check result is picked up at a later call (use it when the graph changes every step);
         # False: never checked (out-of-range ids are then ignored by the build)
         self.validate_edge_index = True
+        self.fuse_layer_norm = True       # normalization='layer_norm': LayerNorm + scalar as one fused pass per direction
 
     # ------------------------------------------------------------------------------
     def _padded_params(self, d: int, r: int):
@@ -310,7 +361,13 @@ class GConvAdapter(nn.Module):
             if out.size(0) > 1:
                 out = self.normalization(out)
         elif isinstance(self.normalization, nn.LayerNorm):
-            out = self.normalization(out)
+            ln = self.normalization
+            if (self.fuse_layer_norm and d % 4 == 0 and d <= 1024 and tuple(ln.normalized_shape) == (d,)
+                    and os.environ.get("GCA_DISABLE_LN_FUSE", "0") != "1"):
+                # LayerNorm + scalar in one pass forward / one pass backward (the scalar is part of the kernel)
+                flat = _LayerNormScaleFunction.apply(out.reshape(-1, d), ln.weight, ln.bias, self.scalar, ln.eps)
+                return flat.reshape(out.shape)
+            out = ln(out)
         if self.normalization is not None and self.scalar is not None:
             out = out * self.scalar
         return out

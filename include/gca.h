@@ -226,6 +226,22 @@ int gca_peer_export(void* ptr, void* handle64 /* host out */);
 int gca_peer_open(const void* handle64 /* host */, void** ptr /* host out */);
 int gca_peer_close(void* ptr);
 
+/* -------- normalization = 'layer_norm' tail (src/finetune/gconv_adapter.py:54-61, 98-106) --------
+ * Y = s * (gamma * (X - mean_row) * rstd_row + beta): torch.nn.LayerNorm over the last dimension (biased variance, eps inside
+ * the square root) followed by the adapter's learnable scalar, one pass forward and one pass backward over [n, d].
+ * gamma / beta / scalar may be NULL (= 1 / 0 / 1).  mean, rstd: [n] floats written by the forward and read by the backward.
+ * X is the forward's input (the output of gca_fwd_hop2_up without scalar).  d % 4 == 0, d <= 1024.
+ * Backward: gX (may be NULL), ggamma / gbeta [d] and gscalar [1] (any may be NULL); scratch of gca_layernorm_scratch_bytes(d)
+ * bytes (256 B aligned) holds the per-CTA partial sums, combined in a fixed order (no atomics). */
+size_t gca_layernorm_scratch_bytes(int32_t d);
+int    gca_layernorm_scale_fwd(const float* X, int64_t ldx, const float* gamma, const float* beta, const float* scalar,
+                               float eps, float* Y, int64_t ldy, float* mean, float* rstd, int32_t n, int32_t d,
+                               gca_stream_t stream);
+int    gca_layernorm_scale_bwd(const float* gY, int64_t ldg, const float* X, int64_t ldx, const float* gamma, const float* beta,
+                               const float* scalar, const float* mean, const float* rstd, float* gX, int64_t ldgx,
+                               float* ggamma, float* gbeta, float* gscalar, void* scratch, int32_t n, int32_t d,
+                               gca_stream_t stream);
+
 /* -------- multi-GPU for a client that owns an NCCL communicator --------
  * The whole partitioned forward / backward of ONE rank: the phases above with an in-place ncclAllGather of each r-wide
  * operand between them and an ncclAllReduce (sum) of the parameter gradients at the end, all on `stream`.
