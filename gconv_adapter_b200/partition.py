@@ -427,8 +427,14 @@ class PartitionedGConvAdapter(GConvAdapter):
                                          self.skip_connection, num_nodes, comm, self._backend)
         if isinstance(self.normalization, nn.LayerNorm):
             ln = self.normalization
-            out = torch.nn.functional.layer_norm(out, ln.normalized_shape, _AllReduceGrad.apply(ln.weight, group),
-                                                 _AllReduceGrad.apply(ln.bias, group), ln.eps)
-            if self.scalar is not None:
-                out = out * _AllReduceGrad.apply(self.scalar, group)
+            w, b = _AllReduceGrad.apply(ln.weight, group), _AllReduceGrad.apply(ln.bias, group)
+            sc = _AllReduceGrad.apply(self.scalar, group) if self.scalar is not None else None
+            d = self.hidden_size
+            if out.is_cuda and self.fuse_layer_norm and d <= 1024 and tuple(ln.normalized_shape) == (d,):
+                from .finetune.gconv_adapter import _LayerNormScaleFunction      # row-local: the fused tail works per shard
+                out = _LayerNormScaleFunction.apply(out, w, b, sc, ln.eps)
+            else:
+                out = torch.nn.functional.layer_norm(out, ln.normalized_shape, w, b, ln.eps)
+                if sc is not None:
+                    out = out * sc
         return out

@@ -307,3 +307,62 @@ def test_nccl_comm_entry_points_match_single_gpu(act):
     out = mgr.dict()
     mp.spawn(_nccl_abi_worker, args=(2, port, 30001, 256, 16, act, out), nprocs=2, join=True)
     assert len(out) == 2
+
+
+def _ln_worker(rank, world, port, n, d, r, out):
+    import torch.distributed as dist
+    from gconv_adapter_b200 import GConvAdapter
+    from gconv_adapter_b200.graphs.csr import GraphCache
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ei = symmetric_random_graph(n, 8 * n, seed=51).cuda()
+        x, g_out, params = make_inputs(n, d, r, seed=52)
+        lo, hi = row_block(n, world, rank)
+
+        def build(cls):
+            m = cls(d, r, normalization="layer_norm", learnable_scalar=True)
+            load_module_params(m, params)
+            with torch.no_grad():
+                m.normalization.weight.copy_(1 + 0.2 * torch.arange(d) / d)
+                m.normalization.bias.fill_(0.03)
+            return m.cuda()
+
+        part = build(PartitionedGConvAdapter)
+        xl = x[lo:hi].cuda().requires_grad_(True)
+        y = part(xl, ei, n)
+        y.backward(g_out[lo:hi].cuda())
+        ref = build(GConvAdapter)
+        ref.graph_cache = GraphCache()
+        xf = x.cuda().requires_grad_(True)
+        yr = ref(xf, ei)
+        yr.backward(g_out.cuda())
+        torch.cuda.synchronize()
+        rel = lambda a, b: ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+        errs = {"y": rel(y.detach(), yr.detach()[lo:hi]), "gx": rel(xl.grad, xf.grad[lo:hi])}
+        for (k, p), (_, q) in zip(sorted(part.named_parameters()), sorted(ref.named_parameters())):
+            if k != "scalar":
+                errs[k] = rel(p.grad, q.grad)
+        out[rank] = errs
+        part.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_layer_norm_matches_single_gpu():
+    """normalization='layer_norm' is row-local: the partitioned module (fused LayerNorm + scalar tail per shard, LayerNorm
+    and scalar gradients summed over the ranks) equals the single-GPU module."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ln_worker, args=(2, port, 20001, 256, 16, out), nprocs=2, join=True)
+    for rank in range(2):
+        for k, v in out[rank].items():
+            assert v <= (1e-5 if k not in ("y", "gx") else 2e-6), (rank, k, v)
