@@ -233,6 +233,20 @@ def products_subrecord(lib, dev, steps=8):
            "gather_bound_bytes": a_gather, "frac_of_measured_peak_on_gather_bound": round(a_gather / 1e6 / ms / peak, 4),
            "phases_ms": {k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in prof.items()},
            "variants": {k: v["variant"] for k, v in prof.items() if v["variant"]}}
+    # dominant kernel of this workload: algorithmic bytes against its measured time, and the DRAM bytes ncu saw for it
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    dom_ms = prof[dom]["ms"] / max(prof[dom]["launches"], 1)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("products", {}).get(dom)
+    except Exception:
+        traffic = None
+    rec["roofline"] = {"bound": "hbm", "kernel": dom, "ms_per_launch": round(dom_ms, 5), "alg_bytes_per_launch": per.get(dom, 0),
+                       "achieved": round(per.get(dom, 0) / 1e6 / dom_ms, 1), "peak": peak, "unit": "GB/s",
+                       "frac": round(per.get(dom, 0) / 1e6 / dom_ms / peak, 4), "traffic": traffic,
+                       "traffic_GBs": round(traffic / 1e6 / dom_ms, 1) if traffic else None,
+                       "note": "r-wide gather on a random graph whose operand is 2.5x the L2: DRAM traffic (ncu) is ~10x the "
+                               "algorithmic bytes and moves at ~90% of the measured peak"}
     del m, eid, xd, gd
     torch.cuda.empty_cache()
     return rec
