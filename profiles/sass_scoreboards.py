@@ -31,7 +31,12 @@ def decode(lines):
 
 if __name__ == "__main__":
     pat = sys.argv[1]
-    lib = sys.argv[2] if len(sys.argv) > 2 else "gconv_adapter_b200/lib/libgca.so"
+    if len(sys.argv) > 2:
+        lib = sys.argv[2]
+    else:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from gconv_adapter_b200.build import lib_path
+        lib = lib_path()
     for name, lines in kernels(lib).items():
         if pat in name:
             print("==", name)
