@@ -50,6 +50,11 @@ def _worker(rank, world, port, n, d, r, kw, out):
         y.backward(g_out[lo:hi])
         res = {"lo": lo, "hi": hi, "y": y.detach(), "gx": xl.grad,
                "grads": {k: p.grad.clone() for k, p in m.named_parameters()}}
+        # collectives inside the step (no fused pushes): capture_step leaves the step to eager launches, on every rank,
+        # and close() is safe to call more than once
+        res["captured"] = m.capture_step(lambda: None)
+        m.close()
+        m.close()
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -77,6 +82,7 @@ def test_partitioned_matches_full_graph_oracle(world, n, kw):
     yr.backward(g_out)
     y = torch.cat([out[k]["y"] for k in range(world)])
     gx = torch.cat([out[k]["gx"] for k in range(world)])
+    assert all(out[k]["captured"] is None for k in range(world))
     assert torch.allclose(y, yr.detach(), rtol=1e-4, atol=1e-5)
     assert torch.allclose(gx, xx.grad, rtol=1e-4, atol=1e-5)
     for k, p in ref.named_parameters():
